@@ -1,0 +1,127 @@
+/* pf_b200.h -- C ABI of the B200-native PerspectiveFields inference engine (libpf_b200.so).
+ *
+ * The reference (jinlinyi/PerspectiveFields) is pure Python and has no FFI boundary of its own: the boundary it
+ * offers is the class perspective2d.PerspectiveFields (perspective2d/perspectivefields.py:121-272).  This header is
+ * what a maintainer binds (ctypes) underneath that class to replace
+ *
+ *     PerspectiveFields.forward                 perspectivefields.py:223-272
+ *       ResizeTransform.apply_image (uint8)     perspectivefields.py:38-46     (pf_forward, images_u8 path)
+ *       (x - pixel_mean) / pixel_std, stack     perspectivefields.py:234-236
+ *       backbone (MiT-B3), ll_enc               mix_transformers.py:449-485, perspectivefields.py:79-83
+ *       persformer_heads.inference/postprocess  persformer_heads.py:73-101, gravity_head.py:139-197,237-261,
+ *                                               latitude_head.py:138-219, utils/utils.py:114-162,483-507
+ *       param_net                               param_network.py:46-69,193-221, convnext.py:140-152,
+ *                                               utils/utils.py:47-91
+ *
+ * Conventions: plain pointers and sizes only; every DEVICE pointer refers to memory on the engine's device that the
+ * caller owns (allocated e.g. through PyTorch); the engine owns nothing but small lookup tables.  All work is
+ * enqueued on the caller's stream and the call returns without synchronising.  Functions return 0 on success and a
+ * negative pf_status otherwise; pf_last_error() gives the message (thread-local).  A handle is not re-entrant.
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with PF_ERR_CUDA.
+ */
+#ifndef PF_B200_H_
+#define PF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PF_ABI_VERSION 1
+
+typedef struct pf_engine* pf_handle;
+
+enum pf_status { PF_OK = 0, PF_ERR_ARG = -1, PF_ERR_CUDA = -2, PF_ERR_WEIGHT = -3, PF_ERR_WORKSPACE = -4 };
+
+enum pf_dtype { PF_F32 = 0, PF_BF16 = 1 };
+
+enum pf_param_net { PF_PARAM_NONE = 0, PF_PARAM_CENTERED = 1 /* ParamNet @320x320 */, PF_PARAM_UNCENTERED = 2 /* ParamNetConvNextRegress @64x64 */ };
+
+/* Model variant (the five yaml files of perspective2d/config/ reduce to these fields). */
+typedef struct pf_model_desc {
+  int gravity_classes;   /* 2 = regression (L2-normalised up-vector), 73 = classification logits            */
+  int latitude_classes;  /* 1 = regression (clamped sin(latitude)),   180 = classification logits           */
+  int param_net;         /* enum pf_param_net                                                               */
+  int param_input_size;  /* MODEL.PARAM_DECODER.INPUT_SIZE for PF_PARAM_UNCENTERED (64)                     */
+  float pixel_mean[3];   /* MODEL.PIXEL_MEAN, channel order of the input image (B, G, R)                    */
+  float pixel_std[3];    /* MODEL.PIXEL_STD                                                                 */
+} pf_model_desc;
+
+/* One inference_batch call.  Exactly one of images_u8 / images_chw is non-NULL. */
+typedef struct pf_batch {
+  int n;                       /* number of images                                                          */
+  /* uint8 path (PerspectiveFields.inference{,_batch}): DEVICE blob of tightly packed HWC uint8 BGR images   */
+  const uint8_t* images_u8;
+  const int64_t* image_offset; /* HOST [n] byte offset of each image in the blob                            */
+  /* float path (PerspectiveFields.forward called directly): DEVICE fp32 [n,3,320,320], already resized      */
+  const float* images_chw;
+  const int32_t* height;       /* HOST [n] original heights ("height" key)                                  */
+  const int32_t* width;        /* HOST [n] original widths  ("width" key)                                   */
+  /* outputs, DEVICE, fp32 */
+  float* pred_gravity;         /* [n, gravity_classes, 320, 320]                                            */
+  float* pred_latitude;        /* [n, latitude_classes, 320, 320]                                           */
+  float* gravity_original;     /* blob; image i occupies [2, H_i, W_i] at gravity_original_offset[i]        */
+  const int64_t* gravity_original_offset;   /* HOST [n], in floats                                         */
+  float* latitude_original;    /* blob; image i occupies [H_i, W_i] at latitude_original_offset[i]          */
+  const int64_t* latitude_original_offset;  /* HOST [n], in floats                                         */
+  float* params;               /* [n, 8]: roll, pitch, vfov|general_vfov (deg), rel_cx, rel_cy, rel_focal, raw x2, 0;
+                                  may be NULL when param_net == PF_PARAM_NONE                               */
+} pf_batch;
+
+int pf_abi_version(void);
+const char* pf_last_error(void);
+
+/* Number of CUDA kernels launched by this library in the calling process so far (all handles). */
+int64_t pf_kernel_launch_count(void);
+
+/* Engine lifetime.  `device` is the CUDA ordinal; the engine makes it current for its own calls. */
+int pf_create(int device, const pf_model_desc* desc, pf_handle* out);
+int pf_destroy(pf_handle h);
+
+/* Register one repacked weight tensor (DEVICE pointer, stays owned by the caller and must outlive the handle).
+ * Names and layouts are listed in perspectivefields_b200/weights.py; pf_finalize checks that all are present. */
+int pf_set_weight(pf_handle h, const char* name, const void* dev_ptr, int64_t numel, int dtype);
+int pf_finalize(pf_handle h);
+
+/* Bytes of DEVICE scratch pf_forward needs for a batch of n images whose largest member has max_h rows. */
+int64_t pf_workspace_bytes(pf_handle h, int n, int max_h);
+
+/* Whole forward of perspectivefields.py:223-272 for one batch, enqueued on `stream` (a cudaStream_t). */
+int pf_forward(pf_handle h, const pf_batch* batch, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Per-launch timing of the GEMM engine with CUDA events on the launch stream (bench.py roofline leg).  pf_profile_read
+ * fills out9[cfg*3 + {0,1,2}] = {milliseconds, algorithmic FLOPs (2*M*N*K), launches} for the three tile configurations
+ * (0: 128x128, 1: 128x64, 2: 128x32) accumulated since the previous read; synchronise the stream first. */
+int pf_profile_enable(pf_handle h, int on);
+int pf_profile_read(pf_handle h, double* out9);
+
+/* Debug taps (tests only): when enabled, intermediates of the next pf_forward are kept (never recycled) and can be
+ * copied out by name (device-to-device, enqueued on `stream`).  Names are listed by pf_debug_name(i). */
+int pf_debug_enable(pf_handle h, int on);
+int pf_debug_count(pf_handle h);
+const char* pf_debug_name(pf_handle h, int i);
+int64_t pf_debug_numel(pf_handle h, const char* name);
+int pf_debug_copy(pf_handle h, const char* name, float* dst_dev, int64_t numel, void* stream);
+
+/* ---- single-operator entry points (unit tests; the same kernels pf_forward launches) -------------------- */
+
+/* Implicit-GEMM conv / linear on NHWC fp32, bf16x3 split precision.  x: [B,H,W,Cin]; whi/wlo: bf16 [N][KH*KW*Cin]
+ * ordered (ky,kx,ci); bias: [N] or NULL; res: [B,OH,OW,N] or NULL; y: [B,OH,OW,N].
+ * y = act(conv(relu_in?(x)) + bias) (+ relu_res?(res));  act: 0 none, 1 ReLU, 2 GELU. */
+int pf_op_conv_gemm(const float* x, int B, int H, int W, int Cin, const void* whi, const void* wlo, const float* bias,
+                    int N, int KH, int KW, int stride, int pad, int in_relu, int act, const float* res, int res_relu,
+                    float* y, void* stream);
+int pf_op_layernorm(const float* x, float* y, int64_t rows, int C, const float* w, const float* b, float eps, void* stream);
+int pf_op_attention(const float* q, const float* kv, float* out, int B, int N, int C, int heads, void* stream);
+int pf_op_dwconv3x3_gelu(const float* x, float* y, int B, int H, int W, int C, const float* w9c, const float* bias, void* stream);
+int pf_op_dwconv7x7(const float* x, float* y, int B, int H, int W, int C, const float* w49c, const float* bias, void* stream);
+int pf_op_upsample2x(const float* x, float* y, int B, int H, int W, int C, void* stream);
+/* Pillow-exact resize + normalise of ONE uint8 HWC image -> [320,320,4] fp32 (b,g,r,0). */
+int pf_op_preprocess(const uint8_t* img_dev, int H, int W, const float* mean3, const float* std3, float* y, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PF_B200_H_ */

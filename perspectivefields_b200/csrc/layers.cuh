@@ -1,0 +1,454 @@
+// CUDA-core kernels of the inference path: stems, LayerNorm, spatial-reduction attention, depthwise convs,
+// x2 bilinear upsample, prediction tails and the ParamNet pooling/regression tail.  All activations NHWC fp32.
+#pragma once
+#include "common.cuh"
+
+namespace pf {
+
+// =====================================================================================================
+// Direct fp32 convolution for the 3-channel stems (K = KH*KW*3 is too small/unaligned for the MMA tile):
+//   patch_embed1.proj  conv7x7/4 p3 3->64 (+bias)            mix_transformers.py:276-282,243-245
+//   ll_enc.conv1+bn1+relu  conv7x7/2 p3 3->64, BN folded      perspectivefields.py:79-83
+//   ConvNeXt stem      conv4x4/4 p0 3->96 (+bias)             convnext.py:88-91
+// in : [B, H, W, ldin] (first 3 channels used); w: [(ky,kx,ci)][COUT]; out: [B, OH, OW, COUT].
+// Block = PIX_PER_BLOCK output pixels of one row x COUT channels; thread = 1 channel x PPT pixels.
+template <int KH, int KW, int STRIDE, int PAD, int COUT, int PPT, int PGROUPS>
+__global__ void __launch_bounds__(COUT* PGROUPS) stem_conv_kernel(const float* __restrict__ in, int ldin, int B, int H, int W,
+                                                                  const float* __restrict__ w, const float* __restrict__ bias,
+                                                                  float* __restrict__ out, int OH, int OW, int relu) {
+  constexpr int PIX = PPT * PGROUPS;                   // output pixels per block (along x)
+  constexpr int IN_W = (PIX - 1) * STRIDE + KW;        // input columns needed
+  __shared__ float s_in[KH][IN_W][3];
+  const int tiles_x = cdiv(OW, PIX);
+  int bid = blockIdx.x;
+  const int tx = bid % tiles_x; bid /= tiles_x;
+  const int oy = bid % OH; const int b = bid / OH;
+  const int ox0 = tx * PIX;
+  const int iy0 = oy * STRIDE - PAD, ix0 = ox0 * STRIDE - PAD;
+  for (int i = threadIdx.x; i < KH * IN_W * 3; i += blockDim.x) {
+    const int c = i % 3, x = (i / 3) % IN_W, y = i / (3 * IN_W);
+    const int iy = iy0 + y, ix = ix0 + x;
+    float v = 0.f;
+    if ((unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W) v = __ldg(in + ((long long)(b * H + iy) * W + ix) * ldin + c);
+    s_in[y][x][c] = v;
+  }
+  __syncthreads();
+  const int co = threadIdx.x % COUT, pg = threadIdx.x / COUT;
+  float acc[PPT];
+  const float bv = bias ? __ldg(bias + co) : 0.f;
+#pragma unroll
+  for (int j = 0; j < PPT; ++j) acc[j] = bv;
+#pragma unroll 1
+  for (int ky = 0; ky < KH; ++ky) {
+#pragma unroll
+    for (int kx = 0; kx < KW; ++kx) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float wv = __ldg(w + ((ky * KW + kx) * 3 + c) * COUT + co);
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) acc[j] = fmaf(s_in[ky][(pg * PPT + j) * STRIDE + kx][c], wv, acc[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < PPT; ++j) {
+    const int ox = ox0 + pg * PPT + j;
+    if (ox < OW) {
+      float v = acc[j];
+      if (relu) v = fmaxf(v, 0.f);
+      out[((long long)(b * OH + oy) * OW + ox) * COUT + co] = v;
+    }
+  }
+}
+
+template <int KH, int KW, int STRIDE, int PAD, int COUT>
+inline cudaError_t stem_conv_launch(const float* in, int ldin, int B, int H, int W, const float* w, const float* bias,
+                                    float* out, int relu, cudaStream_t st) {
+  constexpr int PPT = 4, PGROUPS = (COUT == 64) ? 4 : 2;
+  const int OH = (H + 2 * PAD - KH) / STRIDE + 1, OW = (W + 2 * PAD - KW) / STRIDE + 1;
+  const int tiles_x = cdiv(OW, PPT * PGROUPS);
+  stem_conv_kernel<KH, KW, STRIDE, PAD, COUT, PPT, PGROUPS><<<B * OH * tiles_x, COUT * PGROUPS, 0, st>>>(in, ldin, B, H, W, w, bias, out, OH, OW, relu);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// LayerNorm over the channel dimension of [rows, C] (nn.LayerNorm / F.layer_norm, biased variance, eps inside
+// the sqrt) -- mix_transformers.py:199-200,247,120,457 and convnext.py:172-182 (both data formats reduce to this
+// in NHWC).  One warp per row; two-pass (mean, then centred variance) in registers.
+template <int MAXPER>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ in, float* __restrict__ out, long long rows, int C,
+                                                        const float* __restrict__ gw, const float* __restrict__ gb, float eps) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* x = in + row * C;
+  float v[MAXPER];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXPER; ++i) {
+    const int c = lane + 32 * i;
+    v[i] = c < C ? x[c] : 0.f;
+    s += v[i];
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXPER; ++i) {
+    const int c = lane + 32 * i;
+    const float d = c < C ? v[i] - mean : 0.f;
+    q = fmaf(d, d, q);
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
+  float* y = out + row * C;
+#pragma unroll
+  for (int i = 0; i < MAXPER; ++i) {
+    const int c = lane + 32 * i;
+    if (c < C) y[c] = (v[i] - mean) * rstd * __ldg(gw + c) + __ldg(gb + c);
+  }
+}
+
+inline cudaError_t layernorm_launch(const float* in, float* out, long long rows, int C, const float* w, const float* b, float eps,
+                                    cudaStream_t st) {
+  const unsigned grid = (unsigned)cdivl(rows, 8);
+  if (C <= 128) layernorm_kernel<4><<<grid, 256, 0, st>>>(in, out, rows, C, w, b, eps);
+  else if (C <= 384) layernorm_kernel<12><<<grid, 256, 0, st>>>(in, out, rows, C, w, b, eps);
+  else if (C <= 768) layernorm_kernel<24><<<grid, 256, 0, st>>>(in, out, rows, C, w, b, eps);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// Spatial-reduction attention core: softmax(q k^T * 0.125) v with NKV = 100 keys, head_dim 64
+// (mix_transformers.py:127-131; NKV is 100 at every stage for 320x320 inputs).
+// q: [B, N, C] (head h = channels h*64..), kv: [B, NKV, 2C] (k | v), out: [B, N, C].
+// Block = 128 queries of one (batch, head); K and V staged in shared memory (fp32); one thread per query,
+// two passes over the keys (max, then exp/accumulate) -- fp32 CUDA-core math, exact softmax.
+constexpr int kAttnNkv = 100, kAttnD = 64, kAttnQ = 128;
+__global__ void __launch_bounds__(kAttnQ) attention_kernel(const float* __restrict__ q, const float* __restrict__ kv, float* __restrict__ out,
+                                                           int N, int C, float scale) {
+  extern __shared__ __align__(16) float s_kv[];  // K[100][64], V[100][64]
+  float* sK = s_kv;
+  float* sV = s_kv + kAttnNkv * kAttnD;
+  const int b = blockIdx.z, h = blockIdx.y;
+  const float* kvb = kv + (long long)b * kAttnNkv * 2 * C;
+  for (int i = threadIdx.x; i < kAttnNkv * (kAttnD / 4); i += blockDim.x) {
+    const int j = i / (kAttnD / 4), d4 = i % (kAttnD / 4);
+    const float4 kk = __ldg(reinterpret_cast<const float4*>(kvb + (long long)j * 2 * C + h * kAttnD + d4 * 4));
+    const float4 vv = __ldg(reinterpret_cast<const float4*>(kvb + (long long)j * 2 * C + C + h * kAttnD + d4 * 4));
+    reinterpret_cast<float4*>(sK)[i] = kk;
+    reinterpret_cast<float4*>(sV)[i] = vv;
+  }
+  __syncthreads();
+  const int n = blockIdx.x * kAttnQ + threadIdx.x;
+  if (n >= N) return;
+  float qr[kAttnD];
+  const float* qp = q + ((long long)b * N + n) * C + h * kAttnD;
+#pragma unroll
+  for (int d = 0; d < kAttnD; d += 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(qp + d));
+    qr[d] = t.x * scale; qr[d + 1] = t.y * scale; qr[d + 2] = t.z * scale; qr[d + 3] = t.w * scale;
+  }
+  float mx = -INFINITY;
+  for (int j = 0; j < kAttnNkv; ++j) {
+    const float4* kj = reinterpret_cast<const float4*>(sK + j * kAttnD);
+    float s = 0.f;
+#pragma unroll
+    for (int d4 = 0; d4 < kAttnD / 4; ++d4) {
+      const float4 t = kj[d4];
+      s = fmaf(qr[4 * d4], t.x, s); s = fmaf(qr[4 * d4 + 1], t.y, s); s = fmaf(qr[4 * d4 + 2], t.z, s); s = fmaf(qr[4 * d4 + 3], t.w, s);
+    }
+    mx = fmaxf(mx, s);
+  }
+  float o[kAttnD];
+#pragma unroll
+  for (int d = 0; d < kAttnD; ++d) o[d] = 0.f;
+  float l = 0.f;
+  for (int j = 0; j < kAttnNkv; ++j) {
+    const float4* kj = reinterpret_cast<const float4*>(sK + j * kAttnD);
+    float s = 0.f;
+#pragma unroll
+    for (int d4 = 0; d4 < kAttnD / 4; ++d4) {
+      const float4 t = kj[d4];
+      s = fmaf(qr[4 * d4], t.x, s); s = fmaf(qr[4 * d4 + 1], t.y, s); s = fmaf(qr[4 * d4 + 2], t.z, s); s = fmaf(qr[4 * d4 + 3], t.w, s);
+    }
+    const float pj = expf(s - mx);
+    l += pj;
+    const float4* vj = reinterpret_cast<const float4*>(sV + j * kAttnD);
+#pragma unroll
+    for (int d4 = 0; d4 < kAttnD / 4; ++d4) {
+      const float4 t = vj[d4];
+      o[4 * d4] = fmaf(pj, t.x, o[4 * d4]); o[4 * d4 + 1] = fmaf(pj, t.y, o[4 * d4 + 1]);
+      o[4 * d4 + 2] = fmaf(pj, t.z, o[4 * d4 + 2]); o[4 * d4 + 3] = fmaf(pj, t.w, o[4 * d4 + 3]);
+    }
+  }
+  const float inv = 1.0f / l;
+  float* op = out + ((long long)b * N + n) * C + h * kAttnD;
+#pragma unroll
+  for (int d = 0; d < kAttnD; d += 4)
+    *reinterpret_cast<float4*>(op + d) = make_float4(o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv);
+}
+
+inline cudaError_t attention_launch(const float* q, const float* kv, float* out, int B, int N, int C, int heads, cudaStream_t st) {
+  constexpr int smem = 2 * kAttnNkv * kAttnD * 4;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid(cdiv(N, kAttnQ), heads, B);
+  attention_kernel<<<grid, kAttnQ, smem, st>>>(q, kv, out, N, C, 0.125f);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// Depthwise 3x3 conv (pad 1) + bias + GELU(erf) on NHWC -- Mix-FFN middle, mix_transformers.py:51-52,502-508.
+// w: [9][C], thread = 4 channels of one pixel.
+__global__ void __launch_bounds__(256) dwconv3x3_gelu_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C,
+                                                             const float* __restrict__ w, const float* __restrict__ bias) {
+  const int C4 = C >> 2;
+  const long long total = (long long)B * H * W * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    long long pix = i / C4;
+    const int x = (int)(pix % W); pix /= W;
+    const int y = (int)(pix % H); const int b = (int)(pix / H);
+    float4 acc = __ldg(reinterpret_cast<const float4*>(bias) + c4);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = y + ky - 1;
+      if ((unsigned)iy >= (unsigned)H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = x + kx - 1;
+        if ((unsigned)ix >= (unsigned)W) continue;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(in + ((long long)(b * H + iy) * W + ix) * C) + c4);
+        const float4 k = __ldg(reinterpret_cast<const float4*>(w + (ky * 3 + kx) * C) + c4);
+        acc.x = fmaf(v.x, k.x, acc.x); acc.y = fmaf(v.y, k.y, acc.y); acc.z = fmaf(v.z, k.z, acc.z); acc.w = fmaf(v.w, k.w, acc.w);
+      }
+    }
+    reinterpret_cast<float4*>(out)[i] = make_float4(gelu_erf(acc.x), gelu_erf(acc.y), gelu_erf(acc.z), gelu_erf(acc.w));
+  }
+}
+
+// Depthwise 7x7 conv (pad 3) + bias on NHWC -- ConvNeXt block head, convnext.py:28-30,48.  w: [49][C].
+__global__ void __launch_bounds__(256) dwconv7x7_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C,
+                                                        const float* __restrict__ w, const float* __restrict__ bias) {
+  const int C4 = C >> 2;
+  const long long total = (long long)B * H * W * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    long long pix = i / C4;
+    const int x = (int)(pix % W); pix /= W;
+    const int y = (int)(pix % H); const int b = (int)(pix / H);
+    float4 acc = __ldg(reinterpret_cast<const float4*>(bias) + c4);
+    for (int ky = 0; ky < 7; ++ky) {
+      const int iy = y + ky - 3;
+      if ((unsigned)iy >= (unsigned)H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 7; ++kx) {
+        const int ix = x + kx - 3;
+        if ((unsigned)ix >= (unsigned)W) continue;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(in + ((long long)(b * H + iy) * W + ix) * C) + c4);
+        const float4 k = __ldg(reinterpret_cast<const float4*>(w + (ky * 7 + kx) * C) + c4);
+        acc.x = fmaf(v.x, k.x, acc.x); acc.y = fmaf(v.y, k.y, acc.y); acc.z = fmaf(v.z, k.z, acc.z); acc.w = fmaf(v.w, k.w, acc.w);
+      }
+    }
+    reinterpret_cast<float4*>(out)[i] = acc;
+  }
+}
+
+inline unsigned ew_grid(long long total) {
+  long long g = cdivl(total, 256);
+  const long long cap = 148LL * 32;
+  return (unsigned)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+// =====================================================================================================
+// Bilinear x2 upsample, align_corners=False (decode_head.py:284-286, gravity_head.py:172): taps {0.25, 0.75},
+// edges clamped.  ATen: src = 0.5*(dst+0.5)-0.5 clamped at 0, i1 = min(i0+1, in-1).  NHWC, float4 per thread.
+// `in` channel pitch/offset (ldi, icoff) select one head's half of a 512-channel tensor.
+__global__ void __launch_bounds__(256) upsample2x_kernel(const float* __restrict__ in, int ldi, int icoff, float* __restrict__ out, int ldo, int ocoff,
+                                                         int B, int H, int W, int C) {
+  const int C4 = C >> 2, OH = 2 * H, OW = 2 * W;
+  const long long total = (long long)B * OH * OW * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    long long pix = i / C4;
+    const int x = (int)(pix % OW); pix /= OW;
+    const int y = (int)(pix % OH); const int b = (int)(pix / OH);
+    const float sy = fmaxf(0.5f * (y + 0.5f) - 0.5f, 0.f), sx = fmaxf(0.5f * (x + 0.5f) - 0.5f, 0.f);
+    const int y0 = (int)sy, x0 = (int)sx;
+    const int y1 = y0 + (y0 < H - 1), x1 = x0 + (x0 < W - 1);
+    const float ly = sy - y0, lx = sx - x0, hy = 1.f - ly, hx = 1.f - lx;
+    const float* base = in + (long long)b * H * W * ldi + icoff + c4 * 4;
+    const float4 v00 = __ldg(reinterpret_cast<const float4*>(base + (long long)(y0 * W + x0) * ldi));
+    const float4 v01 = __ldg(reinterpret_cast<const float4*>(base + (long long)(y0 * W + x1) * ldi));
+    const float4 v10 = __ldg(reinterpret_cast<const float4*>(base + (long long)(y1 * W + x0) * ldi));
+    const float4 v11 = __ldg(reinterpret_cast<const float4*>(base + (long long)(y1 * W + x1) * ldi));
+    float4 r;
+    r.x = hy * (hx * v00.x + lx * v01.x) + ly * (hx * v10.x + lx * v11.x);
+    r.y = hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y);
+    r.z = hy * (hx * v00.z + lx * v01.z) + ly * (hx * v10.z + lx * v11.z);
+    r.w = hy * (hx * v00.w + lx * v01.w) + ly * (hx * v10.w + lx * v11.w);
+    *reinterpret_cast<float4*>(out + ((long long)(b * OH + y) * OW + x) * ldo + ocoff + c4 * 4) = r;
+  }
+}
+
+// =====================================================================================================
+// Prediction tail: 1x1 conv 32 -> NC (gravity_head.py:175 / latitude_head.py:174) fused with the head's
+// inference epilogue: mode 1 = F.normalize over the 2 channels (gravity_head.py:192-193, eps 1e-12),
+// mode 2 = clamp to [-1, 1] (latitude_head.py:191-192), mode 0 = raw logits (classification variant).
+// in: [npix, ldi] NHWC (32 channels at offset icoff); out: NCHW [B, NC, HW].  One thread per pixel; weights [NC][32] + bias in smem.
+__global__ void __launch_bounds__(128) pred_tail_kernel(const float* __restrict__ in, int ldi, int icoff, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, float* __restrict__ out, int B, int HW, int NC, int mode) {
+  extern __shared__ float s_w[];  // [NC][32] then [NC]
+  for (int i = threadIdx.x; i < NC * 33; i += blockDim.x) s_w[i] = i < NC * 32 ? __ldg(w + i) : __ldg(bias + i - NC * 32);
+  __syncthreads();
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= (long long)B * HW) return;
+  float f[32];
+#pragma unroll
+  for (int d = 0; d < 32; d += 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(in + pix * ldi + icoff + d));
+    f[d] = t.x; f[d + 1] = t.y; f[d + 2] = t.z; f[d + 3] = t.w;
+  }
+  const int b = (int)(pix / HW), r = (int)(pix % HW);
+  float* o = out + (long long)b * NC * HW + r;
+  if (mode == 1) {
+    float v0 = s_w[64], v1 = s_w[65];
+#pragma unroll
+    for (int d = 0; d < 32; ++d) { v0 = fmaf(f[d], s_w[d], v0); v1 = fmaf(f[d], s_w[32 + d], v1); }
+    const float nrm = fmaxf(sqrtf(v0 * v0 + v1 * v1), 1e-12f);
+    o[0] = v0 / nrm; o[HW] = v1 / nrm;
+  } else {
+    for (int c = 0; c < NC; ++c) {
+      float v = s_w[NC * 32 + c];
+#pragma unroll
+      for (int d = 0; d < 32; ++d) v = fmaf(f[d], s_w[c * 32 + d], v);
+      if (mode == 2) v = fminf(fmaxf(v, -1.f), 1.f);
+      o[(long long)c * HW] = v;
+    }
+  }
+}
+
+// Classification variant: argmax over channels + bin decode (gravity_head.py:243-244 + utils.py:114-130;
+// latitude_head.py:205-208 + utils.py:148-162).  logits NCHW [B, NC, HW] -> field [B, 2 or 1, HW].
+// torch.argmax returns the FIRST maximal index; strict '>' reproduces that.
+__global__ void __launch_bounds__(256) argmax_decode_kernel(const float* __restrict__ logits, float* __restrict__ field, int B, int HW, int NC, int is_gravity) {
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= (long long)B * HW) return;
+  const int b = (int)(pix / HW), r = (int)(pix % HW);
+  const float* lp = logits + (long long)b * NC * HW + r;
+  float best = lp[0];
+  int bi = 0;
+  for (int c = 1; c < NC; ++c) {
+    const float v = __ldg(lp + (long long)c * HW);
+    if (v > best) { best = v; bi = c; }
+  }
+  if (is_gravity) {
+    // angle = (bin * (360/(NC-1)) - 180) / 180 * pi ; bin NC-1 -> (0, 0).  torch evaluates this in fp32 on an int64
+    // tensor promoted to float: bin*5.0 - 180 exact in fp32, then /180*pi.
+    float* o = field + (long long)b * 2 * HW + r;
+    if (bi == NC - 1) { o[0] = 0.f; o[HW] = 0.f; }
+    else {
+      const float ang = ((float)bi * (360.0f / (float)(NC - 1)) - 180.0f) / 180.0f * 3.14159265358979323846f;
+      o[0] = cosf(ang); o[HW] = sinf(ang);
+    }
+  } else {
+    const float bin = 180.0f / (float)NC;
+    field[(long long)b * HW + r] = (-90.0f + (float)bi * bin) + bin * 0.5f;
+  }
+}
+
+// =====================================================================================================
+// ParamNet input: cat(pred_gravity, pred_latitude) (param_network.py:47-49 / 194-197), optionally the nearest
+// 320 -> S sub-sample F.interpolate(images, (S, S)) (src = floor(dst * 320 / S)).  NCHW fields -> NHWC [B,S,S,4].
+__global__ void __launch_bounds__(256) pack_fields_kernel(const float* __restrict__ grav, const float* __restrict__ lat, float* __restrict__ out, int B, int S) {
+  const long long total = (long long)B * S * S;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int x = (int)(i % S), y = (int)((i / S) % S), b = (int)(i / ((long long)S * S));
+  const int sy = (int)floorf((float)y * ((float)kNet / (float)S)), sx = (int)floorf((float)x * ((float)kNet / (float)S));
+  const int sp = min(sy, kNet - 1) * kNet + min(sx, kNet - 1);
+  const float g0 = __ldg(grav + (long long)b * 2 * kNet * kNet + sp);
+  const float g1 = __ldg(grav + (long long)b * 2 * kNet * kNet + kNet * kNet + sp);
+  const float l0 = __ldg(lat + (long long)b * kNet * kNet + sp);
+  reinterpret_cast<float4*>(out)[i] = make_float4(g0, g1, l0, 0.f);
+}
+
+// ParamNet tail: global average pool -> LayerNorm(768, eps 1e-6) -> Linear 768->5 (convnext.py:144-151), then
+// the parameter scaling of param_network.py:54-67 (centered) / :205-220 (uncentered).  One block per image.
+// params out: [B][8] = roll, pitch, vfov|general_vfov, rel_cx, rel_cy, rel_focal, raw2, 0
+// kind 1 (ParamNet): vfov = x2*90, rel_focal = 1/2/tan(x2) (sic), cx = cy = 0.
+// kind 2 (ParamNetConvNextRegress): general_vfov = x2*90, cx = x3, cy = x4, rel_focal = closed-form root of
+//   cos(gvfov) = (p^2+q^2-1)/(2pq), p^2 = f^2+cx^2+(cy+.5)^2, q^2 = f^2+cx^2+(cy-.5)^2 (utils.py:47-91 solves the
+//   same equation with scipy fsolve from f=1.5 and takes abs()).
+__global__ void __launch_bounds__(256) param_tail_kernel(const float* __restrict__ feat, int HW, const float* __restrict__ nw, const float* __restrict__ nb,
+                                                         const float* __restrict__ hw, const float* __restrict__ hb, float* __restrict__ params, int kind) {
+  constexpr int C = 768;
+  __shared__ float s_x[C];
+  __shared__ float s_red[8];
+  __shared__ float s_out[5];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* f = feat + (long long)b * HW * C;
+  for (int c = tid; c < C; c += 256) {
+    float s = 0.f;
+    for (int p = 0; p < HW; ++p) s += f[(long long)p * C + c];
+    s_x[c] = s / (float)HW;
+  }
+  __syncthreads();
+  float s = 0.f;
+  for (int c = tid; c < C; c += 256) s += s_x[c];
+  s = warp_sum(s);
+  if ((tid & 31) == 0) s_red[tid >> 5] = s;
+  __syncthreads();
+  float mean = 0.f;
+  for (int i = 0; i < 8; ++i) mean += s_red[i];
+  mean /= (float)C;
+  __syncthreads();
+  float q = 0.f;
+  for (int c = tid; c < C; c += 256) { const float d = s_x[c] - mean; q = fmaf(d, d, q); }
+  q = warp_sum(q);
+  if ((tid & 31) == 0) s_red[tid >> 5] = q;
+  __syncthreads();
+  float var = 0.f;
+  for (int i = 0; i < 8; ++i) var += s_red[i];
+  const float rstd = 1.0f / sqrtf(var / (float)C + 1e-6f);
+  __syncthreads();
+  for (int c = tid; c < C; c += 256) s_x[c] = (s_x[c] - mean) * rstd * nw[c] + nb[c];
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  if (warp < 5) {
+    float a = 0.f;
+    for (int c = lane; c < C; c += 32) a = fmaf(s_x[c], hw[warp * C + c], a);
+    a = warp_sum(a);
+    if (lane == 0) s_out[warp] = a + hb[warp];
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float* o = params + b * 8;
+    const float x0 = s_out[0], x1 = s_out[1], x2 = s_out[2], x3 = s_out[3], x4 = s_out[4];
+    o[0] = x0 * 90.0f; o[1] = x1 * 90.0f; o[2] = x2 * 90.0f; o[6] = x2; o[7] = 0.f;
+    if (kind == 1) {
+      o[3] = 0.f; o[4] = 0.f;
+      o[5] = 1.0f / 2.0f / tanf(x2);
+    } else {
+      o[3] = x3; o[4] = x4;
+      const double cx = (double)x3, cy = (double)x4;
+      const double gv = (double)o[2] * (3.14159265358979323846 / 180.0);
+      const double c = cos(gv), s2 = 1.0 - c * c;
+      double A;
+      if (s2 < 1e-300) A = INFINITY;
+      else {
+        const double D = 1.0 - s2 * (1.0 + 4.0 * c * c * cy * cy);
+        const double rt = sqrt(fmax(D, 0.0));
+        A = (c >= 0.0 ? (1.0 + rt) : (1.0 - rt)) / (2.0 * s2);
+      }
+      const double f2 = A - cx * cx - cy * cy - 0.25;
+      o[5] = (float)sqrt(f2);   // NaN when the equation has no real root (fsolve does not converge there either)
+    }
+  }
+}
+
+}  // namespace pf

@@ -1,0 +1,771 @@
+// libpf_b200.so -- C ABI (include/pf_b200.h) and forward orchestration of the B200-native PerspectiveFields
+// inference engine.  One engine per device; pf_forward enqueues the whole graph of
+// perspective2d/perspectivefields.py:223-272 on the caller's stream.
+#include "../../include/pf_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+#include "conv_gemm.cuh"
+#include "layers.cuh"
+#include "prepost.cuh"
+
+using namespace pf;
+
+// ----------------------------------------------------------------------------------------------- errors
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CU(expr)                                                                                    \
+  do {                                                                                              \
+    cudaError_t e__ = (expr);                                                                       \
+    if (e__ != cudaSuccess) return fail(PF_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+#define LAUNCHED(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t e__ = (expr);                                                                       \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                             \
+    if (e__ != cudaSuccess) return fail(PF_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+#define TRY(expr)                \
+  do {                           \
+    int r__ = (expr);            \
+    if (r__ != PF_OK) return r__; \
+  } while (0)
+
+// ----------------------------------------------------------------------------------------------- model constants
+static const int kMitDims[4] = {64, 128, 320, 512};
+static const int kMitHeads[4] = {1, 2, 5, 8};
+static const int kMitDepths[4] = {3, 4, 18, 3};
+static const int kMitSr[4] = {8, 4, 2, 1};
+static const int kMitRes[4] = {80, 40, 20, 10};
+static const int kCnxDims[4] = {96, 192, 384, 768};
+static const int kCnxDepths[4] = {3, 3, 9, 3};
+
+struct WeightRef { const void* p; long long numel; int dtype; };
+struct GemmW { const __nv_bfloat16* hi = nullptr; const __nv_bfloat16* lo = nullptr; const float* b = nullptr; };
+struct LnW { const float* w = nullptr; const float* b = nullptr; };
+
+struct MitBlockW { LnW ln1, srln, ln2; GemmW q, sr, kv, proj, fc1, fc2; const float* dw_w; const float* dw_b; };
+struct CnxBlockW { const float* dw_w; const float* dw_b; LnW ln; GemmW pw1, pw2; const float* gamma; };
+
+struct Arena {
+  char* base = nullptr;
+  long long cap = 0, off = 0, peak = 0;
+  bool dry = false, keep = false;  // keep: debug mode, never recycle
+  void* alloc(long long bytes) {
+    off = (off + 255) & ~255LL;
+    void* p = dry ? nullptr : base + off;
+    off += bytes;
+    if (off > peak) peak = off;
+    return p;
+  }
+  float* f(long long n) { return (float*)alloc(n * 4); }
+  long long mark() const { return off; }
+  void release(long long m) { if (!keep) off = m; }
+};
+
+struct pf_engine {
+  int device = 0;
+  pf_model_desc desc{};
+  bool finalized = false;
+  std::unordered_map<std::string, WeightRef> weights;
+  // resolved weights
+  const float *embed1_w, *embed1_b, *llenc_w, *llenc_b;
+  LnW embed_ln[4], stage_norm[4];
+  GemmW embed[4];  // [1..3] used
+  std::vector<MitBlockW> blocks[4];
+  GemmW proc[4];   // composed linear_c{l} o linear_c{l}_proc, both heads side by side (N = 512), index lvl-1
+  GemmW rcu[4][2][2];  // [fusion-1][unit-1][conv-1], grouped over the two heads
+  GemmW conv0, conv1;
+  const float *pred_g_w, *pred_g_b, *pred_l_w, *pred_l_b;
+  const float *pn_stem_w, *pn_stem_b;
+  LnW pn_stem_ln, pn_ds_ln[4], pn_norm;
+  GemmW pn_ds[4];
+  std::vector<CnxBlockW> pn_blocks[4];
+  const float *pn_head_w, *pn_head_b;
+  // Pillow resample tables, cached per input size (device memory owned by the engine)
+  struct DevTable { int ksize; int* bounds; int* coeffs; };
+  std::map<int, DevTable> tables;
+  // per-launch profiling of the GEMM engine (bench.py roofline leg): CUDA events on the launch stream
+  bool profile = false;
+  struct ProfRec { cudaEvent_t a, b; double flops; int cfg; };
+  std::vector<ProfRec> prof;
+  // debug taps
+  bool debug = false;
+  std::vector<std::pair<std::string, std::pair<const float*, long long>>> taps;
+};
+
+// ----------------------------------------------------------------------------------------------- weight lookup
+static int get_w(pf_engine* e, const std::string& name, int dtype, long long numel, const void** out) {
+  auto it = e->weights.find(name);
+  if (it == e->weights.end()) return fail(PF_ERR_WEIGHT, "missing weight '%s'", name.c_str());
+  if (it->second.dtype != dtype) return fail(PF_ERR_WEIGHT, "weight '%s': wrong dtype", name.c_str());
+  if (it->second.numel != numel) return fail(PF_ERR_WEIGHT, "weight '%s': numel %lld, expected %lld", name.c_str(), it->second.numel, numel);
+  *out = it->second.p;
+  return PF_OK;
+}
+static int get_f(pf_engine* e, const std::string& n, long long numel, const float** out) { return get_w(e, n, PF_F32, numel, (const void**)out); }
+static int get_gemm(pf_engine* e, const std::string& n, long long N, long long K, long long nbias, GemmW* g, int groups = 1) {
+  TRY(get_w(e, n + ".whi", PF_BF16, groups * N * K, (const void**)&g->hi));
+  TRY(get_w(e, n + ".wlo", PF_BF16, groups * N * K, (const void**)&g->lo));
+  TRY(get_f(e, n + ".b", groups * nbias, &g->b));
+  return PF_OK;
+}
+static int get_ln(pf_engine* e, const std::string& n, int C, LnW* l) {
+  TRY(get_f(e, n + ".w", C, &l->w));
+  TRY(get_f(e, n + ".b", C, &l->b));
+  return PF_OK;
+}
+
+static int resolve_weights(pf_engine* e) {
+  char nm[128];
+  TRY(get_f(e, "embed1.w", 147 * 64, &e->embed1_w));
+  TRY(get_f(e, "embed1.b", 64, &e->embed1_b));
+  TRY(get_f(e, "llenc.w", 147 * 64, &e->llenc_w));
+  TRY(get_f(e, "llenc.b", 64, &e->llenc_b));
+  for (int s = 0; s < 4; ++s) {
+    const int C = kMitDims[s];
+    snprintf(nm, sizeof nm, "embed%d.ln", s + 1);
+    TRY(get_ln(e, nm, C, &e->embed_ln[s]));
+    if (s > 0) {
+      snprintf(nm, sizeof nm, "embed%d", s + 1);
+      TRY(get_gemm(e, nm, C, 9LL * kMitDims[s - 1], C, &e->embed[s]));
+    }
+    e->blocks[s].resize(kMitDepths[s]);
+    for (int i = 0; i < kMitDepths[s]; ++i) {
+      MitBlockW& b = e->blocks[s][i];
+      char p[64];
+      snprintf(p, sizeof p, "s%d.b%d.", s + 1, i);
+      std::string P(p);
+      TRY(get_ln(e, P + "ln1", C, &b.ln1));
+      TRY(get_gemm(e, P + "q", C, C, C, &b.q));
+      if (kMitSr[s] > 1) {
+        TRY(get_gemm(e, P + "sr", C, (long long)kMitSr[s] * kMitSr[s] * C, C, &b.sr));
+        TRY(get_ln(e, P + "srln", C, &b.srln));
+      }
+      TRY(get_gemm(e, P + "kv", 2 * C, C, 2 * C, &b.kv));
+      TRY(get_gemm(e, P + "proj", C, C, C, &b.proj));
+      TRY(get_ln(e, P + "ln2", C, &b.ln2));
+      TRY(get_gemm(e, P + "fc1", 4 * C, C, 4 * C, &b.fc1));
+      TRY(get_f(e, P + "dw.w", 9LL * 4 * C, &b.dw_w));
+      TRY(get_f(e, P + "dw.b", 4 * C, &b.dw_b));
+      TRY(get_gemm(e, P + "fc2", C, 4 * C, C, &b.fc2));
+    }
+    snprintf(nm, sizeof nm, "s%d.norm", s + 1);
+    TRY(get_ln(e, nm, C, &e->stage_norm[s]));
+  }
+  for (int l = 0; l < 4; ++l) {
+    snprintf(nm, sizeof nm, "head.proc%d", l + 1);
+    TRY(get_gemm(e, nm, 512, 9LL * kMitDims[l], 9 * 512, &e->proc[l]));
+  }
+  for (int f = 0; f < 4; ++f)
+    for (int u = 0; u < 2; ++u) {
+      if (f == 3 && u == 0) continue;  // fusion4 has resConfUnit2 only (gravity_head.py:102)
+      for (int c = 0; c < 2; ++c) {
+        snprintf(nm, sizeof nm, "head.f%d.u%d.c%d", f + 1, u + 1, c + 1);
+        TRY(get_gemm(e, nm, 256, 2304, 256, &e->rcu[f][u][c], 2));
+      }
+    }
+  TRY(get_gemm(e, "head.conv0", 64, 9 * 320, 64, &e->conv0, 2));
+  TRY(get_gemm(e, "head.conv1", 32, 9 * 64, 32, &e->conv1, 2));
+  TRY(get_f(e, "head.pred_g.w", 32LL * e->desc.gravity_classes, &e->pred_g_w));
+  TRY(get_f(e, "head.pred_g.b", e->desc.gravity_classes, &e->pred_g_b));
+  TRY(get_f(e, "head.pred_l.w", 32LL * e->desc.latitude_classes, &e->pred_l_w));
+  TRY(get_f(e, "head.pred_l.b", e->desc.latitude_classes, &e->pred_l_b));
+  if (e->desc.param_net != PF_PARAM_NONE) {
+    TRY(get_f(e, "pn.stem.w", 48 * 96, &e->pn_stem_w));
+    TRY(get_f(e, "pn.stem.b", 96, &e->pn_stem_b));
+    TRY(get_ln(e, "pn.stem.ln", 96, &e->pn_stem_ln));
+    for (int k = 1; k < 4; ++k) {
+      snprintf(nm, sizeof nm, "pn.ds%d.ln", k);
+      TRY(get_ln(e, nm, kCnxDims[k - 1], &e->pn_ds_ln[k]));
+      snprintf(nm, sizeof nm, "pn.ds%d", k);
+      TRY(get_gemm(e, nm, kCnxDims[k], 4LL * kCnxDims[k - 1], kCnxDims[k], &e->pn_ds[k]));
+    }
+    for (int s = 0; s < 4; ++s) {
+      const int C = kCnxDims[s];
+      e->pn_blocks[s].resize(kCnxDepths[s]);
+      for (int j = 0; j < kCnxDepths[s]; ++j) {
+        CnxBlockW& b = e->pn_blocks[s][j];
+        char p[64];
+        snprintf(p, sizeof p, "pn.s%d.b%d.", s, j);
+        std::string P(p);
+        TRY(get_f(e, P + "dw.w", 49LL * C, &b.dw_w));
+        TRY(get_f(e, P + "dw.b", C, &b.dw_b));
+        TRY(get_ln(e, P + "ln", C, &b.ln));
+        TRY(get_gemm(e, P + "pw1", 4 * C, C, 4 * C, &b.pw1));
+        TRY(get_gemm(e, P + "pw2", C, 4 * C, C, &b.pw2));
+        TRY(get_f(e, P + "gamma", C, &b.gamma));
+      }
+    }
+    TRY(get_ln(e, "pn.norm", 768, &e->pn_norm));
+    TRY(get_f(e, "pn.head.w", 5 * 768, &e->pn_head_w));
+    TRY(get_f(e, "pn.head.b", 5, &e->pn_head_b));
+  }
+  return PF_OK;
+}
+
+// ----------------------------------------------------------------------------------------------- op helpers
+struct Fwd {
+  pf_engine* e;
+  Arena ar;
+  cudaStream_t st;
+  bool dry;
+  int n;
+
+  // debug taps: snapshot the tensor into a private buffer (many intermediates are updated in place later)
+  int tap(const char* name, const float* p, long long numel) {
+    if (!e->debug) return PF_OK;
+    float* cp = ar.f(numel);
+    if (dry) return PF_OK;
+    CU(cudaMemcpyAsync(cp, p, numel * 4, cudaMemcpyDeviceToDevice, st));
+    e->taps.push_back({name, {cp, numel}});
+    return PF_OK;
+  }
+  int tapf(const float* p, long long numel, const char* fmt, ...) {
+    if (!e->debug) return PF_OK;
+    char buf[96];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    return tap(buf, p, numel);
+  }
+
+  // generic conv-as-GEMM launch; fills the common fields
+  int gemm(ConvGemmParams p) {
+    if (dry) return PF_OK;
+    const char* msg = conv_gemm_check(p);
+    if (msg) return fail(PF_ERR_ARG, "%s", msg);
+    if (e->profile) {
+      pf_engine::ProfRec r{};
+      CU(cudaEventCreate(&r.a));
+      CU(cudaEventCreate(&r.b));
+      r.flops = 2.0 * (double)p.B * p.OH * p.OW * (double)p.N * (double)p.K * (double)p.groups;
+      r.cfg = conv_gemm_config(p);
+      CU(cudaEventRecord(r.a, st));
+      LAUNCHED(conv_gemm_launch(p, st));
+      CU(cudaEventRecord(r.b, st));
+      e->prof.push_back(r);
+      return PF_OK;
+    }
+    LAUNCHED(conv_gemm_launch(p, st));
+    return PF_OK;
+  }
+  static ConvGemmParams base(const float* A, int lda, int B, int H, int W, int Cin, int KH, int stride, int pad, const GemmW& w, int N,
+                             float* C, int ldc) {
+    ConvGemmParams p{};
+    p.A = A; p.lda = lda; p.B = B; p.H = H; p.W = W; p.Cin = Cin;
+    p.KH = p.KW = KH; p.stride = stride; p.pad = pad;
+    p.OH = (H + 2 * pad - KH) / stride + 1; p.OW = (W + 2 * pad - KH) / stride + 1;
+    p.Whi = w.hi; p.Wlo = w.lo; p.N = N; p.K = KH * KH * Cin;
+    p.bias = w.b; p.bias_mode = w.b ? 1 : 0;
+    p.C = C; p.ldc = ldc; p.groups = 1;
+    return p;
+  }
+  // y[rows, N] = x[rows, K] W^T + b (+res)
+  int linear(const float* x, long long rows, int K, const GemmW& w, int N, float* y, int act = 0, const float* res = nullptr,
+             const float* gamma = nullptr) {
+    ConvGemmParams p = base(x, K, (int)rows, 1, 1, K, 1, 1, 0, w, N, y, N);  // rows as the batch dim: no spatial limit
+    p.act = act; p.res = res; p.ldr = N; p.gamma = gamma;
+    return gemm(p);
+  }
+  int ln(const float* x, float* y, long long rows, int C, const LnW& w, float eps) {
+    if (dry) return PF_OK;
+    LAUNCHED(layernorm_launch(x, y, rows, C, w.w, w.b, eps, st));
+    return PF_OK;
+  }
+};
+
+// ----------------------------------------------------------------------------------------------- the forward graph
+static int get_table(pf_engine* e, int in_size, pf_engine::DevTable* out) {
+  auto it = e->tables.find(in_size);
+  if (it == e->tables.end()) {
+    ResampleTable t = make_resample_table(in_size, kNet);
+    pf_engine::DevTable d{};
+    d.ksize = t.ksize;
+    CU(cudaMalloc(&d.bounds, t.bounds.size() * sizeof(int)));
+    CU(cudaMalloc(&d.coeffs, t.coeffs.size() * sizeof(int)));
+    CU(cudaMemcpy(d.bounds, t.bounds.data(), t.bounds.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d.coeffs, t.coeffs.data(), t.coeffs.size() * sizeof(int), cudaMemcpyHostToDevice));
+    it = e->tables.emplace(in_size, d).first;
+  }
+  *out = it->second;
+  return PF_OK;
+}
+
+static int pre_rows_needed(int H) {  // input rows one block of kPreRows output rows may need
+  const double scale = (double)H / kNet;
+  const double support = scale < 1.0 ? 1.0 : scale;
+  return (int)(kPreRows * scale) + 2 * (int)ceil(support) + 3;
+}
+constexpr int kPreMaxSmemRows = 200 * 1024 / (kNet * 3);
+
+static int run_forward(Fwd& F, const pf_batch* bt, int max_h_for_dry) {
+  pf_engine* e = F.e;
+  const pf_model_desc& D = e->desc;
+  const int n = F.n;
+  const bool dry = F.dry;
+  cudaStream_t st = F.st;
+  Arena& ar = F.ar;
+
+  // ---------------- pre-process: uint8 HWC (any size) -> [n,320,320,4] fp32 normalised -------------------
+  float* x0 = ar.f((long long)n * kNet * kNet * 4);
+  PreImage* d_pre = (PreImage*)ar.alloc((long long)n * sizeof(PreImage));
+  PostImage* d_post = (PostImage*)ar.alloc((long long)n * sizeof(PostImage));
+  if (!dry) {
+    if (bt->images_u8) {
+      std::vector<PreImage> pre(n);
+      int max_h = 1;
+      for (int i = 0; i < n; ++i) {
+        const int H = bt->height[i], W = bt->width[i];
+        if (H < 1 || W < 1) return fail(PF_ERR_ARG, "image %d has size %dx%d", i, H, W);
+        pf_engine::DevTable tx, ty;
+        TRY(get_table(e, W, &tx));
+        TRY(get_table(e, H, &ty));
+        if (ty.ksize + 1 > kPreMaxSmemRows) return fail(PF_ERR_ARG, "image %d is too tall (%d rows) for the resize kernel", i, H);
+        pre[i] = PreImage{bt->image_offset[i], H, W, tx.ksize, ty.ksize, tx.bounds, tx.coeffs, ty.bounds, ty.coeffs};
+        if (H > max_h) max_h = H;
+      }
+      CU(cudaMemcpyAsync(d_pre, pre.data(), n * sizeof(PreImage), cudaMemcpyHostToDevice, st));
+      int rows = pre_rows_needed(max_h);
+      if (rows > kPreMaxSmemRows) rows = kPreMaxSmemRows;
+      const int smem = rows * kNet * 3;
+      static int configured_smem = 0;
+      if (smem > configured_smem) {
+        CU(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem > 48 * 1024 ? smem : 48 * 1024));
+        configured_smem = smem;
+      }
+      LAUNCHED((preprocess_kernel<<<dim3(kNet / kPreRows, n), kNet, smem, st>>>(bt->images_u8, d_pre, x0, D.pixel_mean[0], D.pixel_mean[1],
+                                                                               D.pixel_mean[2], D.pixel_std[0], D.pixel_std[1], D.pixel_std[2], rows),
+                cudaGetLastError()));
+    } else {
+      const long long total = (long long)n * kNet * kNet;
+      LAUNCHED((normalize_chw_kernel<<<(unsigned)cdivl(total, 256), 256, 0, st>>>(bt->images_chw, x0, n, D.pixel_mean[0], D.pixel_mean[1],
+                                                                                 D.pixel_mean[2], D.pixel_std[0], D.pixel_std[1], D.pixel_std[2]),
+                cudaGetLastError()));
+    }
+  }
+  F.tap("pre", x0, (long long)n * kNet * kNet * 4);
+
+  // ---------------- persistent feature maps ---------------------------------------------------------------
+  float* cfeat[4];
+  for (int s = 0; s < 4; ++s) cfeat[s] = ar.f((long long)n * kMitRes[s] * kMitRes[s] * kMitDims[s]);
+  float* ll = ar.f((long long)n * 160 * 160 * 64);
+  if (!dry) LAUNCHED((stem_conv_launch<7, 7, 2, 3, 64>(x0, 4, n, kNet, kNet, e->llenc_w, e->llenc_b, ll, 1, st)));
+  F.tap("ll", ll, (long long)n * 160 * 160 * 64);
+
+  // ---------------- MiT-B3 encoder (mix_transformers.py:449-485) -------------------------------------------
+  for (int s = 0; s < 4; ++s) {
+    const int C = kMitDims[s], R = kMitRes[s], N = R * R, heads = kMitHeads[s], sr = kMitSr[s];
+    const long long rows = (long long)n * N;
+    const long long m = ar.mark();
+    float* x = ar.f(rows * C);
+    float* t1 = ar.f(rows * C);
+    float* q = ar.f(rows * C);
+    float* a = ar.f(rows * C);
+    float* t2 = ar.f((long long)n * 100 * C);
+    float* kv = ar.f((long long)n * 100 * 2 * C);
+    float* h1 = ar.f(rows * 4 * C);
+    float* h2 = ar.f(rows * 4 * C);
+    // OverlapPatchEmbed: conv + LayerNorm(eps 1e-5)
+    if (s == 0) {
+      if (!dry) LAUNCHED((stem_conv_launch<7, 7, 4, 3, 64>(x0, 4, n, kNet, kNet, e->embed1_w, e->embed1_b, t1, 0, st)));
+    } else {
+      ConvGemmParams p = Fwd::base(cfeat[s - 1], kMitDims[s - 1], n, kMitRes[s - 1], kMitRes[s - 1], kMitDims[s - 1], 3, 2, 1, e->embed[s], C, t1, C);
+      TRY(F.gemm(p));
+    }
+    TRY(F.ln(t1, x, rows, C, e->embed_ln[s], 1e-5f));
+    F.tapf(x, rows * C, "mit.s%d.embed", s + 1);
+    for (int i = 0; i < kMitDepths[s]; ++i) {
+      const MitBlockW& b = e->blocks[s][i];
+      // x = x + attn(norm1(x))
+      TRY(F.ln(x, t1, rows, C, b.ln1, 1e-6f));
+      TRY(F.linear(t1, rows, C, b.q, C, q));
+      if (sr > 1) {
+        ConvGemmParams p = Fwd::base(t1, C, n, R, R, C, sr, sr, 0, b.sr, C, t2, C);
+        TRY(F.gemm(p));
+        TRY(F.ln(t2, t2, (long long)n * 100, C, b.srln, 1e-5f));
+        TRY(F.linear(t2, (long long)n * 100, C, b.kv, 2 * C, kv));
+      } else {
+        TRY(F.linear(t1, rows, C, b.kv, 2 * C, kv));
+      }
+      if (!dry) LAUNCHED(attention_launch(q, kv, a, n, N, C, heads, st));
+      TRY(F.linear(a, rows, C, b.proj, C, x, 0, x));
+      F.tapf(x, rows * C, "mit.s%d.b%d.attn", s + 1, i);
+      // x = x + mlp(norm2(x))
+      TRY(F.ln(x, t1, rows, C, b.ln2, 1e-6f));
+      TRY(F.linear(t1, rows, C, b.fc1, 4 * C, h1));
+      if (!dry) LAUNCHED((dwconv3x3_gelu_kernel<<<ew_grid(rows * C), 256, 0, st>>>(h1, h2, n, R, R, 4 * C, b.dw_w, b.dw_b), cudaGetLastError()));
+      TRY(F.linear(h2, rows, 4 * C, b.fc2, C, x, 0, x));
+      F.tapf(x, rows * C, "mit.s%d.b%d", s + 1, i);
+    }
+    TRY(F.ln(x, cfeat[s], rows, C, e->stage_norm[s], 1e-6f));
+    F.tapf(cfeat[s], rows * C, "mit.c%d", s + 1);
+    ar.release(m);
+  }
+
+  // ---------------- decoder heads, gravity (group 0) and latitude (group 1) side by side -------------------
+  // Tensors carry both heads in the channel dimension: [n, h, w, 2*C], head g = channels [g*C, (g+1)*C).
+  float* conv1_out = ar.f((long long)n * kNet * kNet * 64);
+  {
+    const long long m = ar.mark();
+    float* fused = nullptr;  // running top-down feature, [n, r, r, 512] at the resolution of the next level
+    for (int lvl = 4; lvl >= 1; --lvl) {
+      const int r = kMitRes[lvl - 1], Cin = kMitDims[lvl - 1];
+      const long long px = (long long)n * r * r;
+      float* t = ar.f(px * 512);   // linear_c{lvl} o linear_c{lvl}_proc, composed (exact; bias via border classes)
+      float* u = ar.f(px * 512);
+      float* v = ar.f(px * 512);
+      {
+        ConvGemmParams p = Fwd::base(cfeat[lvl - 1], Cin, n, r, r, Cin, 3, 1, 1, e->proc[lvl - 1], 512, t, 512);
+        p.bias_mode = 2;
+        TRY(F.gemm(p));
+        F.tapf(t, px * 512, "head.proc%d", lvl);
+      }
+      auto rcu_conv = [&](const float* A, const GemmW& w, float* Cout, int act, const float* res, int res_relu, const float* res2) {
+        ConvGemmParams p = Fwd::base(A, 512, n, r, r, 256, 3, 1, 1, w, 256, Cout, 512);
+        p.in_relu = (act == 1);  // conv1 of a unit reads relu(x); conv2 reads conv1's (already rectified) output
+        p.act = act;
+        p.res = res; p.ldr = 512; p.res_relu = res_relu;
+        p.res2 = res2; p.ldr2 = 512;
+        p.groups = 2; p.a_gcoff = 256; p.c_gcoff = 256; p.r_gcoff = 256; p.r2_gcoff = 256;
+        p.w_gstride = 256LL * 2304; p.bias_gstride = 256;
+        return F.gemm(p);
+      };
+      const float* o = t;
+      if (lvl < 4) {
+        // output = xs[0] + resConfUnit1(xs[1]);  RCU(x) = conv2(relu(conv1(relu(x)))) + relu(x)   (decode_head.py:244-282)
+        TRY(rcu_conv(t, e->rcu[lvl - 1][0][0], u, 1, nullptr, 0, nullptr));
+        TRY(rcu_conv(u, e->rcu[lvl - 1][0][1], v, 0, t, 1, fused));
+        o = v;
+      }
+      float* w2 = ar.f(px * 512);
+      TRY(rcu_conv(o, e->rcu[lvl - 1][1][0], u, 1, nullptr, 0, nullptr));
+      TRY(rcu_conv(u, e->rcu[lvl - 1][1][1], w2, 0, o, 1, nullptr));
+      float* up = ar.f(px * 4 * 512);
+      if (!dry) LAUNCHED((upsample2x_kernel<<<ew_grid(px * 4 * 128), 256, 0, st>>>(w2, 512, 0, up, 512, 0, n, r, r, 512), cudaGetLastError()));
+      fused = up;
+      F.tapf(up, px * 4 * 512, "head.fusion%d", lvl);
+    }
+    // conv_fuse_conv0 on cat([fused, ll]) (gravity_head.py:170-171), both heads
+    float* c0 = ar.f((long long)n * 160 * 160 * 128);
+    {
+      ConvGemmParams p = Fwd::base(fused, 512, n, 160, 160, 320, 3, 1, 1, e->conv0, 64, c0, 128);
+      p.A2 = ll; p.lda2 = 64; p.a2_coff = 0; p.c_split = 256;
+      p.act = 1;
+      p.groups = 2; p.a_gcoff = 256; p.c_gcoff = 64; p.w_gstride = 64LL * 2880; p.bias_gstride = 64;
+      TRY(F.gemm(p));
+      F.tap("head.conv0", c0, (long long)n * 160 * 160 * 128);
+    }
+    float* c0u = ar.f((long long)n * kNet * kNet * 128);
+    if (!dry) LAUNCHED((upsample2x_kernel<<<ew_grid((long long)n * kNet * kNet * 32), 256, 0, st>>>(c0, 128, 0, c0u, 128, 0, n, 160, 160, 128), cudaGetLastError()));
+    {
+      ConvGemmParams p = Fwd::base(c0u, 128, n, kNet, kNet, 64, 3, 1, 1, e->conv1, 32, conv1_out, 64);
+      p.act = 1;
+      p.groups = 2; p.a_gcoff = 64; p.c_gcoff = 32; p.w_gstride = 32LL * 576; p.bias_gstride = 32;
+      TRY(F.gemm(p));
+      F.tap("head.conv1", conv1_out, (long long)n * kNet * kNet * 64);
+    }
+    ar.release(m);
+  }
+  // prediction tails -> NCHW outputs (returned to the caller)
+  const int HW = kNet * kNet;
+  if (!dry) {
+    const unsigned grid = (unsigned)cdivl((long long)n * HW, 128);
+    LAUNCHED((pred_tail_kernel<<<grid, 128, D.gravity_classes * 33 * 4, st>>>(conv1_out, 64, 0, e->pred_g_w, e->pred_g_b, bt->pred_gravity, n, HW,
+                                                                           D.gravity_classes, D.gravity_classes == 2 ? 1 : 0), cudaGetLastError()));
+    LAUNCHED((pred_tail_kernel<<<grid, 128, D.latitude_classes * 33 * 4, st>>>(conv1_out, 64, 32, e->pred_l_w, e->pred_l_b, bt->pred_latitude, n, HW,
+                                                                            D.latitude_classes, D.latitude_classes == 1 ? 2 : 0), cudaGetLastError()));
+  }
+
+  // ---------------- post-process to the original resolutions ------------------------------------------------
+  const float* vec = dry ? nullptr : bt->pred_gravity;
+  const float* lat = dry ? nullptr : bt->pred_latitude;
+  const bool cls_g = D.gravity_classes != 2, cls_l = D.latitude_classes != 1;
+  if (cls_g) {
+    float* dv = ar.f((long long)n * 2 * HW);
+    if (!dry) LAUNCHED((argmax_decode_kernel<<<(unsigned)cdivl((long long)n * HW, 256), 256, 0, st>>>(bt->pred_gravity, dv, n, HW, D.gravity_classes, 1), cudaGetLastError()));
+    vec = dv;
+  }
+  if (cls_l) {
+    float* dl = ar.f((long long)n * HW);
+    if (!dry) LAUNCHED((argmax_decode_kernel<<<(unsigned)cdivl((long long)n * HW, 256), 256, 0, st>>>(bt->pred_latitude, dl, n, HW, D.latitude_classes, 0), cudaGetLastError()));
+    lat = dl;
+  }
+  if (!dry) {
+    std::vector<PostImage> post(n);
+    long long total = 0;
+    for (int i = 0; i < n; ++i) {
+      post[i] = PostImage{bt->height[i], bt->width[i], bt->gravity_original_offset[i], bt->latitude_original_offset[i], total};
+      total += (long long)bt->height[i] * bt->width[i];
+    }
+    CU(cudaMemcpyAsync(d_post, post.data(), n * sizeof(PostImage), cudaMemcpyHostToDevice, st));
+    LAUNCHED((postprocess_kernel<<<(unsigned)cdivl(total, 256), 256, 0, st>>>(vec, lat, d_post, n, total, bt->gravity_original, bt->latitude_original,
+                                                                             cls_l ? 0 : 1), cudaGetLastError()));
+  }
+
+  // ---------------- ParamNet (ConvNeXt-T on the predicted fields) -------------------------------------------
+  if (D.param_net != PF_PARAM_NONE) {
+    if (cls_g || cls_l) return fail(PF_ERR_ARG, "ParamNet needs regression heads");
+    const int S = D.param_net == PF_PARAM_CENTERED ? kNet : D.param_input_size;
+    float* pin = ar.f((long long)n * S * S * 4);
+    if (!dry) LAUNCHED((pack_fields_kernel<<<(unsigned)cdivl((long long)n * S * S, 256), 256, 0, st>>>(bt->pred_gravity, bt->pred_latitude, pin, n, S), cudaGetLastError()));
+    int r = S / 4;
+    float* x = ar.f((long long)n * r * r * 96);
+    if (!dry) LAUNCHED((stem_conv_launch<4, 4, 4, 0, 96>(pin, 4, n, S, S, e->pn_stem_w, e->pn_stem_b, x, 0, st)));
+    TRY(F.ln(x, x, (long long)n * r * r, 96, e->pn_stem_ln, 1e-6f));
+    for (int s = 0; s < 4; ++s) {
+      const int C = kCnxDims[s];
+      if (s > 0) {
+        // downsample: LayerNorm (channels_first == per-pixel LN in NHWC) + conv2x2/2 (convnext.py:93-99)
+        const int r2 = r / 2;
+        float* y = ar.f((long long)n * r * r * kCnxDims[s - 1]);
+        TRY(F.ln(x, y, (long long)n * r * r, kCnxDims[s - 1], e->pn_ds_ln[s], 1e-6f));
+        float* xn = ar.f((long long)n * r2 * r2 * C);
+        ConvGemmParams p = Fwd::base(y, kCnxDims[s - 1], n, r, r, kCnxDims[s - 1], 2, 2, 0, e->pn_ds[s], C, xn, C);
+        TRY(F.gemm(p));
+        x = xn; r = r2;
+      }
+      const long long rows = (long long)n * r * r;
+      float* y = ar.f(rows * C);
+      float* h = ar.f(rows * 4 * C);
+      for (int j = 0; j < kCnxDepths[s]; ++j) {
+        const CnxBlockW& b = e->pn_blocks[s][j];
+        if (!dry) LAUNCHED((dwconv7x7_kernel<<<ew_grid(rows * C / 4), 256, 0, st>>>(x, y, n, r, r, C, b.dw_w, b.dw_b), cudaGetLastError()));
+        TRY(F.ln(y, y, rows, C, b.ln, 1e-6f));
+        TRY(F.linear(y, rows, C, b.pw1, 4 * C, h, 2));
+        TRY(F.linear(h, rows, 4 * C, b.pw2, C, x, 0, x, b.gamma));
+      }
+      F.tapf(x, rows * C, "cnx.s%d", s);
+    }
+    if (!dry) {
+      if (!bt->params) return fail(PF_ERR_ARG, "params output is NULL");
+      LAUNCHED((param_tail_kernel<<<n, 256, 0, st>>>(x, r * r, e->pn_norm.w, e->pn_norm.b, e->pn_head_w, e->pn_head_b, bt->params, D.param_net), cudaGetLastError()));
+    }
+  }
+  (void)max_h_for_dry;
+  return PF_OK;
+}
+
+// ----------------------------------------------------------------------------------------------- C ABI
+extern "C" {
+
+int pf_abi_version(void) { return PF_ABI_VERSION; }
+const char* pf_last_error(void) { return g_err.c_str(); }
+int64_t pf_kernel_launch_count(void) { return g_launches.load(); }
+
+int pf_create(int device, const pf_model_desc* desc, pf_handle* out) {
+  if (!desc || !out) return fail(PF_ERR_ARG, "pf_create: null argument");
+  if (!((desc->gravity_classes == 2 || desc->gravity_classes == 73) && (desc->latitude_classes == 1 || desc->latitude_classes == 180)))
+    return fail(PF_ERR_ARG, "pf_create: unsupported head widths %d/%d", desc->gravity_classes, desc->latitude_classes);
+  if (desc->param_net < 0 || desc->param_net > 2) return fail(PF_ERR_ARG, "pf_create: bad param_net");
+  if (desc->param_net == PF_PARAM_UNCENTERED && (desc->param_input_size < 32 || desc->param_input_size > kNet || desc->param_input_size % 32))
+    return fail(PF_ERR_ARG, "pf_create: param_input_size must be a multiple of 32 in [32, 320]");
+  int count = 0;
+  CU(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count) return fail(PF_ERR_CUDA, "pf_create: no CUDA device %d (found %d)", device, count);
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(PF_ERR_CUDA, "pf_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  pf_engine* e = new pf_engine();
+  e->device = device;
+  e->desc = *desc;
+  *out = e;
+  return PF_OK;
+}
+
+int pf_destroy(pf_handle h) {
+  if (!h) return PF_OK;
+  cudaSetDevice(h->device);
+  for (auto& kv : h->tables) { cudaFree(kv.second.bounds); cudaFree(kv.second.coeffs); }
+  delete h;
+  return PF_OK;
+}
+
+int pf_set_weight(pf_handle h, const char* name, const void* dev_ptr, int64_t numel, int dtype) {
+  if (!h || !name || !dev_ptr) return fail(PF_ERR_ARG, "pf_set_weight: null argument");
+  if (((uintptr_t)dev_ptr & 15) != 0) return fail(PF_ERR_ARG, "pf_set_weight: '%s' is not 16-byte aligned", name);
+  h->weights[name] = WeightRef{dev_ptr, numel, dtype};
+  h->finalized = false;
+  return PF_OK;
+}
+
+int pf_finalize(pf_handle h) {
+  if (!h) return fail(PF_ERR_ARG, "pf_finalize: null handle");
+  TRY(resolve_weights(h));
+  h->finalized = true;
+  return PF_OK;
+}
+
+int64_t pf_workspace_bytes(pf_handle h, int n, int max_h) {
+  if (!h || n < 1) return fail(PF_ERR_ARG, "pf_workspace_bytes: bad argument");
+  Fwd F{h, Arena{}, nullptr, true, n};
+  F.ar.dry = true;
+  F.ar.keep = h->debug;
+  int r = run_forward(F, nullptr, max_h);
+  if (r != PF_OK) return r;
+  return F.ar.peak + 4096;
+}
+
+int pf_forward(pf_handle h, const pf_batch* bt, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!h || !bt || !workspace) return fail(PF_ERR_ARG, "pf_forward: null argument");
+  if (!h->finalized) return fail(PF_ERR_WEIGHT, "pf_forward: pf_finalize has not succeeded");
+  if (bt->n < 1) return fail(PF_ERR_ARG, "pf_forward: empty batch");
+  if ((bt->images_u8 != nullptr) == (bt->images_chw != nullptr)) return fail(PF_ERR_ARG, "pf_forward: exactly one of images_u8 / images_chw");
+  if (bt->images_u8 && !bt->image_offset) return fail(PF_ERR_ARG, "pf_forward: image_offset is NULL");
+  if (!bt->height || !bt->width || !bt->pred_gravity || !bt->pred_latitude || !bt->gravity_original || !bt->latitude_original ||
+      !bt->gravity_original_offset || !bt->latitude_original_offset)
+    return fail(PF_ERR_ARG, "pf_forward: null input/output pointer");
+  CU(cudaSetDevice(h->device));
+  Fwd F{h, Arena{}, (cudaStream_t)stream, false, bt->n};
+  F.ar.base = (char*)workspace;
+  F.ar.cap = workspace_bytes;
+  F.ar.keep = h->debug;
+  {  // capacity check with a dry run (cheap: no launches)
+    Fwd T{h, Arena{}, nullptr, true, bt->n};
+    T.ar.dry = true; T.ar.keep = h->debug;
+    TRY(run_forward(T, nullptr, 0));
+    if (T.ar.peak > workspace_bytes) return fail(PF_ERR_WORKSPACE, "pf_forward: workspace %lld B < required %lld B", (long long)workspace_bytes, T.ar.peak);
+  }
+  if (((uintptr_t)workspace & 255) != 0) return fail(PF_ERR_ARG, "pf_forward: workspace must be 256-byte aligned");
+  h->taps.clear();
+  return run_forward(F, bt, 0);
+}
+
+int pf_profile_enable(pf_handle h, int on) {
+  if (!h) return fail(PF_ERR_ARG, "null handle");
+  h->profile = on != 0;
+  return PF_OK;
+}
+// out[cfg*3 + {0,1,2}] = {milliseconds, algorithmic FLOPs, launches} per GEMM tile configuration (3 configs),
+// accumulated since the last read; the caller must have synchronised the stream.
+int pf_profile_read(pf_handle h, double* out9) {
+  if (!h || !out9) return fail(PF_ERR_ARG, "pf_profile_read: null argument");
+  for (int i = 0; i < 9; ++i) out9[i] = 0.0;
+  for (auto& r : h->prof) {
+    float ms = 0.f;
+    CU(cudaEventSynchronize(r.b));
+    CU(cudaEventElapsedTime(&ms, r.a, r.b));
+    out9[r.cfg * 3 + 0] += ms;
+    out9[r.cfg * 3 + 1] += r.flops;
+    out9[r.cfg * 3 + 2] += 1.0;
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  h->prof.clear();
+  return PF_OK;
+}
+
+int pf_debug_enable(pf_handle h, int on) {
+  if (!h) return fail(PF_ERR_ARG, "null handle");
+  h->debug = on != 0;
+  h->taps.clear();
+  return PF_OK;
+}
+int pf_debug_count(pf_handle h) { return h ? (int)h->taps.size() : 0; }
+const char* pf_debug_name(pf_handle h, int i) { return (h && i >= 0 && i < (int)h->taps.size()) ? h->taps[i].first.c_str() : ""; }
+int64_t pf_debug_numel(pf_handle h, const char* name) {
+  if (!h || !name) return -1;
+  for (auto& t : h->taps) if (t.first == name) return t.second.second;
+  return -1;
+}
+int pf_debug_copy(pf_handle h, const char* name, float* dst, int64_t numel, void* stream) {
+  if (!h || !name || !dst) return fail(PF_ERR_ARG, "pf_debug_copy: null argument");
+  for (auto& t : h->taps)
+    if (t.first == name) {
+      if (numel != t.second.second) return fail(PF_ERR_ARG, "pf_debug_copy: '%s' has %lld elements", name, t.second.second);
+      CU(cudaMemcpyAsync(dst, t.second.first, numel * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+      return PF_OK;
+    }
+  return fail(PF_ERR_ARG, "pf_debug_copy: no tap '%s'", name);
+}
+
+// ---- single-operator entry points ------------------------------------------------------------------------
+int pf_op_conv_gemm(const float* x, int B, int H, int W, int Cin, const void* whi, const void* wlo, const float* bias, int N, int KH, int KW,
+                    int stride, int pad, int in_relu, int act, const float* res, int res_relu, float* y, void* stream) {
+  ConvGemmParams p{};
+  p.A = x; p.lda = Cin; p.B = B; p.H = H; p.W = W; p.Cin = Cin;
+  p.KH = KH; p.KW = KW; p.stride = stride; p.pad = pad;
+  p.OH = (H + 2 * pad - KH) / stride + 1; p.OW = (W + 2 * pad - KW) / stride + 1;
+  p.in_relu = in_relu;
+  p.Whi = (const __nv_bfloat16*)whi; p.Wlo = (const __nv_bfloat16*)wlo; p.N = N; p.K = KH * KW * Cin;
+  p.bias = bias; p.bias_mode = bias ? 1 : 0; p.act = act;
+  p.res = res; p.ldr = N; p.res_relu = res_relu;
+  p.C = y; p.ldc = N; p.groups = 1;
+  const char* msg = conv_gemm_check(p);
+  if (msg) return fail(PF_ERR_ARG, "%s", msg);
+  LAUNCHED(conv_gemm_launch(p, (cudaStream_t)stream));
+  return PF_OK;
+}
+int pf_op_layernorm(const float* x, float* y, int64_t rows, int C, const float* w, const float* b, float eps, void* stream) {
+  LAUNCHED(layernorm_launch(x, y, rows, C, w, b, eps, (cudaStream_t)stream));
+  return PF_OK;
+}
+int pf_op_attention(const float* q, const float* kv, float* out, int B, int N, int C, int heads, void* stream) {
+  if (C != heads * kAttnD) return fail(PF_ERR_ARG, "pf_op_attention: head_dim must be 64");
+  LAUNCHED(attention_launch(q, kv, out, B, N, C, heads, (cudaStream_t)stream));
+  return PF_OK;
+}
+int pf_op_dwconv3x3_gelu(const float* x, float* y, int B, int H, int W, int C, const float* w, const float* bias, void* stream) {
+  if (C % 4) return fail(PF_ERR_ARG, "C %% 4");
+  LAUNCHED((dwconv3x3_gelu_kernel<<<ew_grid((long long)B * H * W * C / 4), 256, 0, (cudaStream_t)stream>>>(x, y, B, H, W, C, w, bias), cudaGetLastError()));
+  return PF_OK;
+}
+int pf_op_dwconv7x7(const float* x, float* y, int B, int H, int W, int C, const float* w, const float* bias, void* stream) {
+  if (C % 4) return fail(PF_ERR_ARG, "C %% 4");
+  LAUNCHED((dwconv7x7_kernel<<<ew_grid((long long)B * H * W * C / 4), 256, 0, (cudaStream_t)stream>>>(x, y, B, H, W, C, w, bias), cudaGetLastError()));
+  return PF_OK;
+}
+int pf_op_upsample2x(const float* x, float* y, int B, int H, int W, int C, void* stream) {
+  if (C % 4) return fail(PF_ERR_ARG, "C %% 4");
+  LAUNCHED((upsample2x_kernel<<<ew_grid((long long)B * H * W * C), 256, 0, (cudaStream_t)stream>>>(x, C, 0, y, C, 0, B, H, W, C), cudaGetLastError()));
+  return PF_OK;
+}
+int pf_op_preprocess(const uint8_t* img, int H, int W, const float* mean3, const float* std3, float* y, void* stream) {
+  // standalone tables (not cached): test entry point only
+  ResampleTable tx = make_resample_table(W, kNet), ty = make_resample_table(H, kNet);
+  if (ty.ksize + 1 > kPreMaxSmemRows) return fail(PF_ERR_ARG, "image too tall");
+  int *bx, *cx, *by, *cy;
+  PreImage* d;
+  CU(cudaMalloc(&bx, tx.bounds.size() * 4)); CU(cudaMalloc(&cx, tx.coeffs.size() * 4));
+  CU(cudaMalloc(&by, ty.bounds.size() * 4)); CU(cudaMalloc(&cy, ty.coeffs.size() * 4));
+  CU(cudaMalloc(&d, sizeof(PreImage)));
+  CU(cudaMemcpy(bx, tx.bounds.data(), tx.bounds.size() * 4, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(cx, tx.coeffs.data(), tx.coeffs.size() * 4, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(by, ty.bounds.data(), ty.bounds.size() * 4, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(cy, ty.coeffs.data(), ty.coeffs.size() * 4, cudaMemcpyHostToDevice));
+  PreImage pi{0, H, W, tx.ksize, ty.ksize, bx, cx, by, cy};
+  CU(cudaMemcpy(d, &pi, sizeof pi, cudaMemcpyHostToDevice));
+  int rows = pre_rows_needed(H);
+  if (rows > kPreMaxSmemRows) rows = kPreMaxSmemRows;
+  const int smem = rows * kNet * 3;
+  CU(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem > 48 * 1024 ? smem : 48 * 1024));
+  LAUNCHED((preprocess_kernel<<<dim3(kNet / kPreRows, 1), kNet, smem, (cudaStream_t)stream>>>(img, d, y, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2], rows),
+            cudaGetLastError()));
+  CU(cudaStreamSynchronize((cudaStream_t)stream));
+  cudaFree(bx); cudaFree(cx); cudaFree(by); cudaFree(cy); cudaFree(d);
+  return PF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,191 @@
+// HBM-bound ends of the path: Pillow-exact uint8 resize + normalisation (pre) and resample-to-original (post).
+#pragma once
+#include <math.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace pf {
+
+// =====================================================================================================
+// Pre-process.  Reference: perspectivefields.py:38-46 (PIL.Image.resize((320,320), BILINEAR) on uint8) and
+// :234-236 ((x - pixel_mean) / pixel_std).  Pillow's resampler (src/libImaging/Resample.c, third-party) is an
+// antialiased separable triangle filter with 22-bit fixed-point coefficients, horizontal pass first, each pass
+// rounded to uint8.  The coefficient tables are built on the host in double precision exactly as Pillow's
+// precompute_coeffs/normalize_coeffs_8bpc do; the kernel is pure integer arithmetic and therefore bit-exact.
+constexpr int kPrecisionBits = 32 - 8 - 2;
+
+struct ResampleTable {  // host-side, for one (in_size -> 320) axis
+  int in_size = 0, ksize = 0;
+  std::vector<int> bounds;  // [320][2] = (xmin, count)
+  std::vector<int> coeffs;  // [320][ksize]
+};
+
+inline ResampleTable make_resample_table(int in_size, int out_size) {
+  ResampleTable t;
+  t.in_size = in_size;
+  const double scale = (double)in_size / (double)out_size;
+  const double filterscale = scale < 1.0 ? 1.0 : scale;
+  const double support = 1.0 * filterscale;  // bilinear (triangle) filter support = 1
+  t.ksize = (int)ceil(support) * 2 + 1;
+  t.bounds.assign((size_t)out_size * 2, 0);
+  t.coeffs.assign((size_t)out_size * t.ksize, 0);
+  std::vector<double> k((size_t)t.ksize);
+  const double ss = 1.0 / filterscale;
+  for (int xx = 0; xx < out_size; ++xx) {
+    const double center = (xx + 0.5) * scale;
+    int xmin = (int)(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = (int)(center + support + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    const int n = xmax - xmin;
+    double ww = 0.0;
+    for (int x = 0; x < n; ++x) {
+      double a = (x + xmin - center + 0.5) * ss;
+      if (a < 0.0) a = -a;
+      const double w = a < 1.0 ? 1.0 - a : 0.0;
+      k[x] = w;
+      ww += w;
+    }
+    for (int x = 0; x < n; ++x) {
+      double v = k[x];
+      if (ww != 0.0) v /= ww;
+      t.coeffs[(size_t)xx * t.ksize + x] = v < 0 ? (int)(-0.5 + v * (1 << kPrecisionBits)) : (int)(0.5 + v * (1 << kPrecisionBits));
+    }
+    t.bounds[2 * xx] = xmin;
+    t.bounds[2 * xx + 1] = n;
+  }
+  return t;
+}
+
+struct PreImage {          // per image, device-visible
+  long long offset;        // byte offset of the HWC uint8 image in the input blob
+  int H, W;
+  int ksx, ksy;            // table widths
+  const int* bx; const int* cx;   // horizontal tables (depend on W)
+  const int* by; const int* cy;   // vertical tables   (depend on H)
+};
+
+constexpr int kPreRows = 8;  // output rows per block
+
+// grid = (320 / kPreRows, n_images), block = 320 threads (one per output column).
+// dyn smem = rows_needed * 320 * 3 bytes for the horizontally resampled input rows of this tile.
+// out: [n, 320, 320, 4] fp32 NHWC, channels (b, g, r, 0), value = (u8 - mean[c]) / std[c].
+__global__ void __launch_bounds__(kNet) preprocess_kernel(const unsigned char* __restrict__ blob, const PreImage* __restrict__ imgs, float* __restrict__ out,
+                                                          float m0, float m1, float m2, float s0, float s1, float s2, int max_rows) {
+  extern __shared__ unsigned char s_h[];  // [rows][320][3]
+  const PreImage im = imgs[blockIdx.y];
+  const int oy0 = blockIdx.x * kPreRows;
+  const int x = threadIdx.x;
+  const unsigned char* src = blob + im.offset;
+  const int xmin = im.bx[2 * x], xn = im.bx[2 * x + 1];
+  const int* kx = im.cx + (long long)x * im.ksx;
+  for (int r0 = 0; r0 < kPreRows;) {
+    // process as many output rows as fit in smem (normally all kPreRows at once)
+    int rcount = 0;
+    const int in_first = im.by[2 * (oy0 + r0)];
+    int in_last = in_first;
+    while (r0 + rcount < kPreRows) {
+      const int o = oy0 + r0 + rcount;
+      const int last = im.by[2 * o] + im.by[2 * o + 1];
+      if (last - in_first > max_rows && rcount > 0) break;
+      in_last = last;
+      ++rcount;
+    }
+    const int nrows = in_last - in_first;
+    // horizontal pass: input rows [in_first, in_last) -> uint8 [nrows][320][3]
+    for (int r = 0; r < nrows; ++r) {
+      const unsigned char* row = src + ((long long)(in_first + r) * im.W + xmin) * 3;
+      int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
+      for (int t = 0; t < xn; ++t) {
+        const int k = kx[t];
+        a0 += row[3 * t] * k; a1 += row[3 * t + 1] * k; a2 += row[3 * t + 2] * k;
+      }
+      unsigned char* d = s_h + (r * kNet + x) * 3;
+      d[0] = (unsigned char)min(max(a0 >> kPrecisionBits, 0), 255);
+      d[1] = (unsigned char)min(max(a1 >> kPrecisionBits, 0), 255);
+      d[2] = (unsigned char)min(max(a2 >> kPrecisionBits, 0), 255);
+    }
+    __syncthreads();
+    // vertical pass
+    for (int rr = 0; rr < rcount; ++rr) {
+      const int o = oy0 + r0 + rr;
+      const int ymin = im.by[2 * o] - in_first, yn = im.by[2 * o + 1];
+      const int* ky = im.cy + (long long)o * im.ksy;
+      int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
+      for (int t = 0; t < yn; ++t) {
+        const int k = ky[t];
+        const unsigned char* d = s_h + ((ymin + t) * kNet + x) * 3;
+        a0 += d[0] * k; a1 += d[1] * k; a2 += d[2] * k;
+      }
+      const float v0 = (float)min(max(a0 >> kPrecisionBits, 0), 255);
+      const float v1 = (float)min(max(a1 >> kPrecisionBits, 0), 255);
+      const float v2 = (float)min(max(a2 >> kPrecisionBits, 0), 255);
+      reinterpret_cast<float4*>(out)[((long long)blockIdx.y * kNet + o) * kNet + x] =
+          make_float4((v0 - m0) / s0, (v1 - m1) / s1, (v2 - m2) / s2, 0.f);
+    }
+    __syncthreads();
+    r0 += rcount;
+  }
+}
+
+// Lower entry (perspectivefields.py:223-236 called directly): images already resized, fp32 CHW [n,3,320,320].
+__global__ void __launch_bounds__(256) normalize_chw_kernel(const float* __restrict__ in, float* __restrict__ out, int n,
+                                                            float m0, float m1, float m2, float s0, float s1, float s2) {
+  const long long total = (long long)n * kNet * kNet;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long b = i / (kNet * kNet), p = i % (kNet * kNet);
+  const float* s = in + b * 3 * kNet * kNet + p;
+  reinterpret_cast<float4*>(out)[i] = make_float4((s[0] - m0) / s0, (s[kNet * kNet] - m1) / s1, (s[2 * kNet * kNet] - m2) / s2, 0.f);
+}
+
+// =====================================================================================================
+// Post-process.  Reference: gravity_head.py:237-261, latitude_head.py:195-219, utils/utils.py:483-507.
+//   gravity : vec * (W/320, H/320) -> bilinear (align_corners=False, no antialias) to (H, W) -> F.normalize(dim=0)
+//   latitude: bilinear to (H, W) -> asin -> rad2deg          (regression)   |  bilinear of decoded degrees (classification)
+// ATen upsample_bilinear2d: scale = (float)320 / out; src = scale*(dst+0.5)-0.5, clamped at 0; i1 = i0 + (i0 < 319).
+struct PostImage {
+  int H, W;
+  long long g_off;  // float offset of this image's [2,H,W] block in the gravity_original blob
+  long long l_off;  // float offset of this image's [H,W] block in the latitude_original blob
+  long long pix0;   // first global output-pixel index of this image (prefix sum of H*W)
+};
+
+// One thread per output pixel of the whole batch; the image is found by binary search over pix0.
+__global__ void __launch_bounds__(256) postprocess_kernel(const float* __restrict__ vec, const float* __restrict__ lat, const PostImage* __restrict__ imgs, int n,
+                                                          long long total, float* __restrict__ g_out, float* __restrict__ l_out, int lat_is_sin) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (imgs[mid].pix0 <= i) lo = mid; else hi = mid - 1;
+  }
+  const PostImage im = imgs[lo];
+  const int p = (int)(i - im.pix0);
+  const int y = p / im.W, x = p - y * im.W;
+  const float sch = (float)kNet / (float)im.H, scw = (float)kNet / (float)im.W;
+  const float sy = fmaxf(sch * ((float)y + 0.5f) - 0.5f, 0.f), sx = fmaxf(scw * ((float)x + 0.5f) - 0.5f, 0.f);
+  const int y0 = min((int)sy, kNet - 1), x0 = min((int)sx, kNet - 1);
+  const int y1 = y0 + (y0 < kNet - 1), x1 = x0 + (x0 < kNet - 1);
+  const float ly = sy - (float)y0, lx = sx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
+  const int i00 = y0 * kNet + x0, i01 = y0 * kNet + x1, i10 = y1 * kNet + x0, i11 = y1 * kNet + x1;
+  const float* v0 = vec + (long long)lo * 2 * kNet * kNet;
+  const float* v1 = v0 + kNet * kNet;
+  const float* lp = lat + (long long)lo * kNet * kNet;
+  // the reference scales the field before resampling: vec * [[W/320],[H/320]] (float32 tensor built from python doubles)
+  const float fx = (float)((double)im.W / (double)kNet), fy = (float)((double)im.H / (double)kNet);
+  const float gx = hy * (hx * (v0[i00] * fx) + lx * (v0[i01] * fx)) + ly * (hx * (v0[i10] * fx) + lx * (v0[i11] * fx));
+  const float gy = hy * (hx * (v1[i00] * fy) + lx * (v1[i01] * fy)) + ly * (hx * (v1[i10] * fy) + lx * (v1[i11] * fy));
+  const float nrm = fmaxf(sqrtf(gx * gx + gy * gy), 1e-12f);
+  const long long HW = (long long)im.H * im.W;
+  g_out[im.g_off + p] = gx / nrm;
+  g_out[im.g_off + HW + p] = gy / nrm;
+  float lv = hy * (hx * lp[i00] + lx * lp[i01]) + ly * (hx * lp[i10] + lx * lp[i11]);
+  if (lat_is_sin) lv = asinf(lv) * (180.0f / 3.14159265358979323846f);
+  l_out[im.l_off + p] = lv;
+}
+
+}  // namespace pf

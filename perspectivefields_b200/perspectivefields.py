@@ -1,0 +1,293 @@
+"""Drop-in for ``perspective2d.PerspectiveFields`` (reference: perspective2d/perspectivefields.py:121-272) whose
+whole forward runs in libpf_b200.so (hand-written sm_100a CUDA, C ABI in include/pf_b200.h).
+
+Kept from the reference surface: ``PerspectiveFields(version)``, ``.eval()``, ``.cuda()/.to()``, ``.device``,
+``.versions()``, ``.inference(img_bgr)``, ``.inference_batch(list)``, ``.forward(batched_inputs)``,
+``.state_dict()/.load_state_dict()`` with the reference's key names, attributes ``version``, ``param_on``, ``cfg``,
+``input_format``; result dictionaries with the same keys, order, shapes and dtypes.  There is no CPU path: the model
+must live on a CUDA device (B200) and libpf_b200.so must be built, otherwise inference raises.
+"""
+import ctypes
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _native
+from .checkpoint import checkpoint_schema, default_state, load_zoo_checkpoint
+from .variants import PIXEL_MEAN, PIXEL_STD, RESIZE, VARIANTS, make_cfg, model_zoo
+from .weights import repack
+
+_NET = RESIZE[0]
+
+
+class _Engine:
+    """One libpf_b200 handle + its device-resident repacked weights and scratch, for one CUDA device."""
+
+    def __init__(self, device, version, ref_state):
+        self.L = _native.lib()
+        self.device = device
+        cfg = VARIANTS[version]
+        desc = _native.pf_model_desc()
+        desc.gravity_classes, desc.latitude_classes = cfg["gravity_classes"], cfg["latitude_classes"]
+        desc.param_net = {None: _native.PF_PARAM_NONE, "ParamNet": _native.PF_PARAM_CENTERED,
+                          "ParamNetConvNextRegress": _native.PF_PARAM_UNCENTERED}[cfg["param_net"]]
+        desc.param_input_size = cfg["input_size"]
+        desc.pixel_mean[:] = PIXEL_MEAN
+        desc.pixel_std[:] = PIXEL_STD
+        self.handle = ctypes.c_void_p()
+        _native.check(self.L.pf_create(device.index, ctypes.byref(desc), ctypes.byref(self.handle)))
+        self.tensors = {}
+        for name, t in repack(ref_state, cfg).items():
+            d = t.to(device)
+            self.tensors[name] = d  # keeps the device memory alive for the lifetime of the handle
+            dt = _native.PF_BF16 if d.dtype == torch.bfloat16 else _native.PF_F32
+            _native.check(self.L.pf_set_weight(self.handle, name.encode(), d.data_ptr(), d.numel(), dt))
+        _native.check(self.L.pf_finalize(self.handle))
+        self.workspace = None
+        self.pinned = None
+        self.pinned_event = None
+        self.dev_blob = None
+
+    def close(self):
+        if self.handle:
+            self.L.pf_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _workspace(self, n, max_h):
+        need = _native.check(self.L.pf_workspace_bytes(self.handle, n, max_h))
+        if self.workspace is None or self.workspace.numel() < need:
+            self.workspace = None
+            self.workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self.workspace
+
+    def stage_images(self, imgs):
+        """Host uint8 images -> one pinned blob -> one async H2D copy.  Returns (device blob, offsets)."""
+        sizes = [im.size for im in imgs]
+        offsets = np.zeros(len(imgs), np.int64)
+        np.cumsum(sizes[:-1], out=offsets[1:])
+        total = int(sum(sizes))
+        if self.pinned is None or self.pinned.numel() < total:
+            self.pinned = torch.empty(max(total, 1 << 20), dtype=torch.uint8).pin_memory()
+            self.dev_blob = torch.empty(self.pinned.numel(), dtype=torch.uint8, device=self.device)
+            self.pinned_event = None
+        if self.pinned_event is not None:
+            self.pinned_event.synchronize()  # the previous batch's H2D must have drained before the blob is reused
+        host = self.pinned.numpy()
+        for im, off in zip(imgs, offsets):
+            host[off:off + im.size] = im.reshape(-1)
+        self.dev_blob[:total].copy_(self.pinned[:total], non_blocking=True)
+        self.pinned_event = torch.cuda.Event()
+        self.pinned_event.record()
+        return self.dev_blob, offsets
+
+    def forward(self, n, heights, widths, blob=None, offsets=None, chw=None):
+        dev = self.device
+        h = np.ascontiguousarray(heights, np.int32)
+        w = np.ascontiguousarray(widths, np.int32)
+        hw = h.astype(np.int64) * w.astype(np.int64)
+        g_off = np.zeros(n, np.int64)
+        l_off = np.zeros(n, np.int64)
+        np.cumsum(2 * hw[:-1], out=g_off[1:])
+        np.cumsum(hw[:-1], out=l_off[1:])
+        out = {
+            "pred_gravity": torch.empty((n, self.gravity_classes, _NET, _NET), dtype=torch.float32, device=dev),
+            "pred_latitude": torch.empty((n, self.latitude_classes, _NET, _NET), dtype=torch.float32, device=dev),
+            "gravity_original": torch.empty(int(2 * hw.sum()), dtype=torch.float32, device=dev),
+            "latitude_original": torch.empty(int(hw.sum()), dtype=torch.float32, device=dev),
+            "params": torch.empty((n, 8), dtype=torch.float32, device=dev),
+            "g_off": g_off, "l_off": l_off, "h": h, "w": w,
+        }
+        ws = self._workspace(n, int(h.max()))
+        bt = _native.pf_batch()
+        bt.n = n
+        i64p, i32p = ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int32)
+        if blob is not None:
+            offsets = np.ascontiguousarray(offsets, np.int64)
+            bt.images_u8 = blob.data_ptr()
+            bt.image_offset = offsets.ctypes.data_as(i64p)
+        else:
+            bt.images_chw = chw.data_ptr()
+        bt.height, bt.width = h.ctypes.data_as(i32p), w.ctypes.data_as(i32p)
+        bt.pred_gravity, bt.pred_latitude = out["pred_gravity"].data_ptr(), out["pred_latitude"].data_ptr()
+        bt.gravity_original, bt.gravity_original_offset = out["gravity_original"].data_ptr(), g_off.ctypes.data_as(i64p)
+        bt.latitude_original, bt.latitude_original_offset = out["latitude_original"].data_ptr(), l_off.ctypes.data_as(i64p)
+        bt.params = out["params"].data_ptr()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _native.check(self.L.pf_forward(self.handle, ctypes.byref(bt), ws.data_ptr(), ws.numel(), stream))
+        return out
+
+
+class PerspectiveFields(nn.Module):
+    def __init__(self, version="Paramnet-360Cities-edina-centered"):
+        super().__init__()
+        zoo = model_zoo[version]  # KeyError for unknown versions, like the reference (perspectivefields.py:127)
+        self.version = version
+        self.param_on = zoo["param"]
+        self.cfg = make_cfg(version)
+        self._variant = VARIANTS[version]
+        self.register_buffer("pixel_mean", torch.tensor(PIXEL_MEAN).view(-1, 1, 1), False)
+        self.register_buffer("pixel_std", torch.tensor(PIXEL_STD).view(-1, 1, 1), False)
+        self.vis_period = self.cfg.VIS_PERIOD
+        self.freeze = self.cfg.MODEL.FREEZE
+        self.debug_on = self.cfg.DEBUG_ON
+        self.input_format = self.cfg.INPUT.FORMAT
+        self._schema = dict(checkpoint_schema(version))
+        self._ref_state = default_state(version)   # reference-layout weights, host side
+        self._engine = None
+        self.training = False
+        self._init_weights()
+
+    # ------------------------------------------------------------------------------------------ module plumbing
+    @property
+    def device(self):
+        return self.pixel_mean.device
+
+    @staticmethod
+    def versions():
+        for key in model_zoo:
+            print(f"{key}")
+            print(f"   - {model_zoo[key]['description']}")
+
+    def train(self, mode=True):
+        if mode:
+            raise RuntimeError("perspectivefields_b200.PerspectiveFields is inference-only: call .eval()")
+        return super().train(False)
+
+    def state_dict(self, *args, **kwargs):
+        """The reference's key layout (backbone.*, ll_enc.*, persformer_heads.*, param_net.backbone.*)."""
+        return {k: v.clone() for k, v in self._ref_state.items()}
+
+    def load_state_dict(self, state_dict, strict=True, assign=False):
+        missing = [k for k in self._schema if k not in state_dict]
+        unexpected = [k for k in state_dict if k not in self._schema]
+        errors = []
+        for k, v in state_dict.items():
+            if k in self._schema:
+                if tuple(v.shape) != tuple(self._schema[k]):
+                    errors.append(f"size mismatch for {k}: checkpoint {tuple(v.shape)} vs model {tuple(self._schema[k])}")
+        if strict and (missing or unexpected):
+            errors.append(f"missing keys {missing[:5]}..., unexpected keys {unexpected[:5]}...")
+        if errors:
+            raise RuntimeError("Error(s) in loading state_dict for PerspectiveFields:\n\t" + "\n\t".join(errors))
+        for k, v in state_dict.items():
+            if k in self._schema:
+                self._ref_state[k] = v.detach().to("cpu", self._ref_state[k].dtype).clone()
+        self._drop_engine()
+        return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
+
+    def _init_weights(self):
+        """perspectivefields.py:178-192."""
+        state_dict = load_zoo_checkpoint(model_zoo[self.version]["weights"])
+        self.load_state_dict(state_dict, strict=False)  # a no-op on the {"model": ...} wrapper, as in the reference
+        if state_dict:
+            self.load_state_dict(state_dict["model"], strict=False)
+
+    def _drop_engine(self):
+        if self._engine is not None:
+            self._engine.close()
+            self._engine = None
+
+    def _get_engine(self):
+        dev = self.device
+        if dev.type != "cuda":
+            raise RuntimeError("perspectivefields_b200 has no CPU path: move the model to a B200 with .cuda() first")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        if self._engine is None or self._engine.device != dev:
+            self._drop_engine()
+            with torch.cuda.device(dev):
+                eng = _Engine(dev, self.version, self._ref_state)
+            eng.gravity_classes = self._variant["gravity_classes"]
+            eng.latitude_classes = self._variant["latitude_classes"]
+            self._engine = eng
+        return self._engine
+
+    # ------------------------------------------------------------------------------------------ inference API
+    @torch.no_grad()
+    def inference(self, img_bgr):
+        return self.inference_batch([img_bgr])[0]
+
+    @torch.no_grad()
+    def inference_batch(self, img_bgr_list):
+        imgs = []
+        for im in img_bgr_list:
+            im = np.asarray(im)
+            if im.dtype != np.uint8 or im.ndim != 3 or im.shape[2] != 3:
+                raise TypeError("inference expects (H, W, 3) uint8 BGR images; got %s %s" % (im.dtype, im.shape))
+            if self.input_format == "RGB":
+                im = im[:, :, ::-1]
+            imgs.append(np.ascontiguousarray(im))
+        if not imgs:
+            return []
+        eng = self._get_engine()
+        with torch.cuda.device(eng.device):
+            blob, offsets = eng.stage_images(imgs)
+            out = eng.forward(len(imgs), [im.shape[0] for im in imgs], [im.shape[1] for im in imgs], blob=blob, offsets=offsets)
+        return self._assemble(out)
+
+    @torch.no_grad()
+    def forward(self, batched_inputs):
+        """perspectivefields.py:223-272: ``[{"image": float32 [3,320,320] (resized, un-normalised), "height", "width"}]``."""
+        if any(k in batched_inputs[0] for k in ("gt_gravity", "gt_latitude")) and self.training:
+            raise RuntimeError("training is not supported")
+        eng = self._get_engine()
+        with torch.cuda.device(eng.device):
+            chw = torch.stack([x["image"].to(eng.device, torch.float32) for x in batched_inputs]).contiguous()
+            if tuple(chw.shape[1:]) != (3, _NET, _NET):
+                raise ValueError("forward expects images already resized to [3, 320, 320]")
+            out = eng.forward(len(batched_inputs), [int(x["height"]) for x in batched_inputs],
+                              [int(x["width"]) for x in batched_inputs], chw=chw)
+        return self._assemble(out)
+
+    def _assemble(self, out):
+        """Result dictionaries: keys and order of persformer_heads.py:83-101 + param_network.py:54-67 / 205-220 +
+        perspectivefields.py:261-271."""
+        v = self._variant
+        n = out["pred_gravity"].shape[0]
+        res = []
+        P = out["params"]
+        zeros = torch.zeros_like(P[:, 0]) if v["param_net"] == "ParamNet" else None
+        for i in range(n):
+            h, w = int(out["h"][i]), int(out["w"][i])
+            go, lo = int(out["g_off"][i]), int(out["l_off"][i])
+            d = {
+                "pred_gravity": out["pred_gravity"][i],
+                "pred_gravity_original": out["gravity_original"][go:go + 2 * h * w].view(2, h, w),
+                "pred_latitude": out["pred_latitude"][i],
+                "pred_latitude_original": out["latitude_original"][lo:lo + h * w].view(h, w),
+                "pred_latitude_original_mode": "deg",
+            }
+            if v["param_net"] == "ParamNet":
+                d.update({"pred_roll": P[i, 0], "pred_pitch": P[i, 1], "pred_vfov": P[i, 2], "pred_rel_focal": P[i, 5],
+                          "pred_general_vfov": P[i, 2], "pred_rel_cx": zeros[i], "pred_rel_cy": zeros[i]})
+            elif v["param_net"] == "ParamNetConvNextRegress":
+                d.update({"pred_roll": P[i, 0], "pred_pitch": P[i, 1], "pred_general_vfov": P[i, 2], "pred_rel_cx": P[i, 3],
+                          "pred_rel_cy": P[i, 4], "pred_rel_focal": P[i, 5]})
+            res.append(d)
+        return res
+
+    # ------------------------------------------------------------------------------------------ test hooks
+    def debug_taps(self, enable=True):
+        eng = self._get_engine()
+        _native.check(eng.L.pf_debug_enable(eng.handle, 1 if enable else 0))
+        eng.workspace = None
+
+    def read_taps(self):
+        eng = self._get_engine()
+        L, out = eng.L, {}
+        stream = torch.cuda.current_stream(eng.device).cuda_stream
+        for i in range(L.pf_debug_count(eng.handle)):
+            name = L.pf_debug_name(eng.handle, i)
+            numel = L.pf_debug_numel(eng.handle, name)
+            t = torch.empty(numel, dtype=torch.float32, device=eng.device)
+            _native.check(L.pf_debug_copy(eng.handle, name, t.data_ptr(), numel, stream))
+            out[name.decode()] = t
+        torch.cuda.synchronize(eng.device)
+        return out

@@ -1,0 +1,99 @@
+"""CPU: host-side logic of the product package -- zoo/config surface, checkpoint schema and loader semantics,
+weight repack algebra (composition + border-class bias, BN folding, hi/lo split), result assembly rules."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import pf_test_util as U
+from oracle import schema as oschema
+from oracle import weights_gen as wg
+from perspectivefields_b200 import checkpoint, variants, weights
+
+
+def test_zoo_matches_reference_surface():
+    assert list(variants.model_zoo) == ["Paramnet-360Cities-edina-centered", "Paramnet-360Cities-edina-uncentered",
+                                        "PersNet-360Cities", "PersNet_Paramnet-GSV-uncentered", "PersNet_Paramnet-GSV-centered"]
+    for k, v in variants.model_zoo.items():
+        assert set(v) == {"weights", "config_file", "param", "description"}
+        assert v["weights"].startswith("https://huggingface.co/spaces/jinlinyi/PerspectiveFields/resolve/main/models/")
+        assert v["param"] == (variants.VARIANTS[k]["param_net"] is not None)
+
+
+@pytest.mark.parametrize("version", list(variants.VARIANTS))
+def test_schema_equals_oracle_schema(version):
+    assert checkpoint.checkpoint_schema(version) == oschema.state_dict_schema(version)
+
+
+def test_split_hi_lo_precision():
+    w = torch.randn(1000, dtype=torch.float64)
+    hi, lo = weights.split_hi_lo(w)
+    assert hi.dtype == lo.dtype == torch.bfloat16
+    assert ((hi.double() + lo.double() - w).abs() / w.abs()).max() < 2 ** -15
+
+
+def test_repack_composition_and_bn_fold():
+    ver = "Paramnet-360Cities-edina-uncentered"
+    sd = wg.synth_state_dict(ver, 1)
+    rp = weights.repack(sd, variants.VARIANTS[ver])
+    # composed linear_c2 o linear_c2_proc of the latitude head, incl. border-class bias
+    p = "persformer_heads.latitude_head."
+    x = torch.randn(1, 128, 7, 9)
+    t = F.linear(x.flatten(2).transpose(1, 2), sd[p + "linear_c2.proj.weight"], sd[p + "linear_c2.proj.bias"]).permute(0, 2, 1).reshape(1, -1, 7, 9)
+    ref = F.conv2d(t, sd[p + "linear_c2_proc.weight"], sd[p + "linear_c2_proc.bias"], padding=1).double()
+    W = (rp["head.proc2.whi"].double() + rp["head.proc2.wlo"].double())[256:].reshape(256, 3, 3, 128).permute(0, 3, 1, 2)
+    got = F.conv2d(x.double(), W, None, padding=1)
+    b = rp["head.proc2.b"].reshape(9, 512)[:, 256:].double()
+    for y in range(7):
+        for xx in range(9):
+            cls = (0 if y == 0 else (2 if y == 6 else 1)) * 3 + (0 if xx == 0 else (2 if xx == 8 else 1))
+            got[0, :, y, xx] += b[cls]
+    assert U.rel_err(got, ref) < 2e-5
+    # BN folded into the low-level encoder conv
+    img = torch.randn(1, 3, 32, 32) * 50
+    ref = F.relu(F.batch_norm(F.conv2d(img, sd["ll_enc.conv1.weight"], None, stride=2, padding=3), sd["ll_enc.bn1.running_mean"],
+                              sd["ll_enc.bn1.running_var"], sd["ll_enc.bn1.weight"], sd["ll_enc.bn1.bias"], False, 0.1, 1e-5))
+    wf = rp["llenc.w"].reshape(7, 7, 3, 64).permute(3, 2, 0, 1)
+    got = F.relu(F.conv2d(img, wf, rp["llenc.b"], stride=2, padding=3))
+    assert U.rel_err(got, ref) < 1e-5
+    # every GEMM layer has hi/lo/bias, K multiple of 32
+    for k in rp:
+        if k.endswith(".whi"):
+            assert k[:-4] + ".wlo" in rp and k[:-4] + ".b" in rp
+
+
+def test_model_surface_without_gpu():
+    m, sd = U.make_model("PersNet_Paramnet-GSV-centered", seed=2, device=None)
+    assert m.version == "PersNet_Paramnet-GSV-centered" and m.param_on is True and m.input_format == "BGR"
+    assert m.cfg.MODEL.RECOVER_RPF is True and m.cfg.MODEL.RECOVER_PP is False and m.cfg.DATALOADER.RESIZE == [320, 320]
+    got = m.state_dict()
+    assert list(got) == [k for k, _ in oschema.state_dict_schema(m.version)]
+    assert all(torch.equal(got[k], sd[k]) for k in sd)
+    with pytest.raises(RuntimeError):
+        m.train()
+    assert m.eval() is m
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m.inference(np.zeros((8, 8, 3), np.uint8))
+    with pytest.raises(KeyError):
+        type(m)("no-such-version")
+    # strict=False tolerance + shape check, as torch does
+    r = m.load_state_dict({"backbone.norm1.weight": torch.ones(64), "extra": torch.ones(1)}, strict=False)
+    assert "extra" in r.unexpected_keys and len(r.missing_keys) == len(got) - 1
+    with pytest.raises(RuntimeError, match="size mismatch"):
+        m.load_state_dict({"backbone.norm1.weight": torch.ones(65)}, strict=False)
+
+
+def test_compat_alias():
+    import sys
+
+    from perspectivefields_b200 import compat
+
+    sys.modules.pop("perspective2d", None)
+    sys.modules.pop("perspective2d.perspectivefields", None)
+    pkg = compat.install()
+    from perspective2d import PerspectiveFields  # noqa
+    from perspective2d.perspectivefields import model_zoo  # noqa
+
+    assert PerspectiveFields is pkg.PerspectiveFields and "PersNet-360Cities" in model_zoo
+    sys.modules.pop("perspective2d", None)
+    sys.modules.pop("perspective2d.perspectivefields", None)
