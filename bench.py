@@ -191,7 +191,7 @@ def main():
     sampler.active = False
     ms = e0.elapsed_time(e1)
     launches = L.pf_kernel_launch_count() - launches0
-    prof = (ctypes.c_double * 9)()
+    prof = (ctypes.c_double * 12)()
     _native.check(L.pf_profile_read(eng.handle, prof))
     _native.check(L.pf_profile_enable(eng.handle, 0))
     clocks = sampler.stop()

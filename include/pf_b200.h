@@ -92,10 +92,14 @@ int64_t pf_workspace_bytes(pf_handle h, int n, int max_h);
 int pf_forward(pf_handle h, const pf_batch* batch, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Per-launch timing of the GEMM engine with CUDA events on the launch stream (bench.py roofline leg).  pf_profile_read
- * fills out9[cfg*3 + {0,1,2}] = {milliseconds, algorithmic FLOPs (2*M*N*K), launches} for the three tile configurations
- * (0: 128x128, 1: 128x64, 2: 128x32) accumulated since the previous read; synchronise the stream first. */
+ * fills out12[cfg*3 + {0,1,2}] = {milliseconds, algorithmic FLOPs (2*M*N*K), launches} for the four engine configurations
+ * (0: HMMA 128x128, 1: HMMA 128x64, 2: HMMA 128x32, 3: tcgen05 128x256) accumulated since the previous read; synchronise the stream first. */
 int pf_profile_enable(pf_handle h, int on);
-int pf_profile_read(pf_handle h, double* out9);
+int pf_profile_read(pf_handle h, double* out12);
+
+/* Engine options.  "tcgen05" = 1 routes the convolutions whose output width is a multiple of 256 (the decoder heads'
+ * 3x3 convolutions, ~55 % of the FLOPs) to the tcgen05/TMEM kernel instead of the warp-level HMMA kernel. */
+int pf_set_option(pf_handle h, const char* name, int value);
 
 /* Debug taps (tests only): when enabled, intermediates of the next pf_forward are kept (never recycled) and can be
  * copied out by name (device-to-device, enqueued on `stream`).  Names are listed by pf_debug_name(i). */
@@ -112,7 +116,7 @@ int pf_debug_copy(pf_handle h, const char* name, float* dst_dev, int64_t numel, 
  * y = act(conv(relu_in?(x)) + bias) (+ relu_res?(res));  act: 0 none, 1 ReLU, 2 GELU. */
 int pf_op_conv_gemm(const float* x, int B, int H, int W, int Cin, const void* whi, const void* wlo, const float* bias,
                     int N, int KH, int KW, int stride, int pad, int in_relu, int act, const float* res, int res_relu,
-                    float* y, void* stream);
+                    float* y, int engine /* 0 = HMMA kernel, 1 = tcgen05 kernel */, void* stream);
 int pf_op_layernorm(const float* x, float* y, int64_t rows, int C, const float* w, const float* b, float eps, void* stream);
 int pf_op_attention(const float* q, const float* kv, float* out, int B, int N, int C, int heads, void* stream);
 int pf_op_dwconv3x3_gelu(const float* x, float* y, int B, int H, int W, int C, const float* w9c, const float* bias, void* stream);

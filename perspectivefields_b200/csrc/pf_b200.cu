@@ -16,6 +16,7 @@
 
 #include "common.cuh"
 #include "conv_gemm.cuh"
+#include "conv_gemm_tc.cuh"
 #include "layers.cuh"
 #include "prepost.cuh"
 
@@ -106,6 +107,7 @@ struct pf_engine {
   struct DevTable { int ksize; int* bounds; int* coeffs; };
   std::map<int, DevTable> tables;
   // per-launch profiling of the GEMM engine (bench.py roofline leg): CUDA events on the launch stream
+  bool use_tc = false;   // route eligible convolutions (N % 256 == 0) to the tcgen05/TMEM engine
   bool profile = false;
   struct ProfRec { cudaEvent_t a, b; double flops; int cfg; };
   std::vector<ProfRec> prof;
@@ -256,19 +258,20 @@ struct Fwd {
     if (dry) return PF_OK;
     const char* msg = conv_gemm_check(p);
     if (msg) return fail(PF_ERR_ARG, "%s", msg);
+    const bool tc = e->use_tc && conv_gemm_tc_eligible(p);
     if (e->profile) {
       pf_engine::ProfRec r{};
       CU(cudaEventCreate(&r.a));
       CU(cudaEventCreate(&r.b));
       r.flops = 2.0 * (double)p.B * p.OH * p.OW * (double)p.N * (double)p.K * (double)p.groups;
-      r.cfg = conv_gemm_config(p);
+      r.cfg = tc ? 3 : conv_gemm_config(p);
       CU(cudaEventRecord(r.a, st));
-      LAUNCHED(conv_gemm_launch(p, st));
+      LAUNCHED(tc ? conv_gemm_tc_launch(p, st) : conv_gemm_launch(p, st));
       CU(cudaEventRecord(r.b, st));
       e->prof.push_back(r);
       return PF_OK;
     }
-    LAUNCHED(conv_gemm_launch(p, st));
+    LAUNCHED(tc ? conv_gemm_tc_launch(p, st) : conv_gemm_launch(p, st));
     return PF_OK;
   }
   static ConvGemmParams base(const float* A, int lda, int B, int H, int W, int Cin, int KH, int stride, int pad, const GemmW& w, int N,
@@ -658,11 +661,16 @@ int pf_profile_enable(pf_handle h, int on) {
   h->profile = on != 0;
   return PF_OK;
 }
-// out[cfg*3 + {0,1,2}] = {milliseconds, algorithmic FLOPs, launches} per GEMM tile configuration (3 configs),
+int pf_set_option(pf_handle h, const char* name, int value) {
+  if (!h || !name) return fail(PF_ERR_ARG, "pf_set_option: null argument");
+  if (!strcmp(name, "tcgen05")) { h->use_tc = value != 0; return PF_OK; }
+  return fail(PF_ERR_ARG, "pf_set_option: unknown option '%s'", name);
+}
+// out[cfg*3 + {0,1,2}] = {milliseconds, algorithmic FLOPs, launches} per GEMM engine configuration (4 configs),
 // accumulated since the last read; the caller must have synchronised the stream.
 int pf_profile_read(pf_handle h, double* out9) {
   if (!h || !out9) return fail(PF_ERR_ARG, "pf_profile_read: null argument");
-  for (int i = 0; i < 9; ++i) out9[i] = 0.0;
+  for (int i = 0; i < 12; ++i) out9[i] = 0.0;
   for (auto& r : h->prof) {
     float ms = 0.f;
     CU(cudaEventSynchronize(r.b));
@@ -703,7 +711,7 @@ int pf_debug_copy(pf_handle h, const char* name, float* dst, int64_t numel, void
 
 // ---- single-operator entry points ------------------------------------------------------------------------
 int pf_op_conv_gemm(const float* x, int B, int H, int W, int Cin, const void* whi, const void* wlo, const float* bias, int N, int KH, int KW,
-                    int stride, int pad, int in_relu, int act, const float* res, int res_relu, float* y, void* stream) {
+                    int stride, int pad, int in_relu, int act, const float* res, int res_relu, float* y, int engine, void* stream) {
   ConvGemmParams p{};
   p.A = x; p.lda = Cin; p.B = B; p.H = H; p.W = W; p.Cin = Cin;
   p.KH = KH; p.KW = KW; p.stride = stride; p.pad = pad;
@@ -713,6 +721,12 @@ int pf_op_conv_gemm(const float* x, int B, int H, int W, int Cin, const void* wh
   p.bias = bias; p.bias_mode = bias ? 1 : 0; p.act = act;
   p.res = res; p.ldr = N; p.res_relu = res_relu;
   p.C = y; p.ldc = N; p.groups = 1;
+  if (engine == 1) {
+    const char* msg = conv_gemm_tc_check(p);
+    if (msg) return fail(PF_ERR_ARG, "%s", msg);
+    LAUNCHED(conv_gemm_tc_launch(p, (cudaStream_t)stream));
+    return PF_OK;
+  }
   const char* msg = conv_gemm_check(p);
   if (msg) return fail(PF_ERR_ARG, "%s", msg);
   LAUNCHED(conv_gemm_launch(p, (cudaStream_t)stream));

@@ -141,6 +141,7 @@ class PerspectiveFields(nn.Module):
         self._schema = dict(checkpoint_schema(version))
         self._ref_state = default_state(version)   # reference-layout weights, host side
         self._engine = None
+        self._options = {}
         self.training = False
         self._init_weights()
 
@@ -206,6 +207,8 @@ class PerspectiveFields(nn.Module):
                 eng = _Engine(dev, self.version, self._ref_state)
             eng.gravity_classes = self._variant["gravity_classes"]
             eng.latitude_classes = self._variant["latitude_classes"]
+            for k, v in self._options.items():
+                _native.check(eng.L.pf_set_option(eng.handle, k.encode(), v))
             self._engine = eng
         return self._engine
 
@@ -272,6 +275,12 @@ class PerspectiveFields(nn.Module):
                           "pred_rel_cy": P[i, 4], "pred_rel_focal": P[i, 5]})
             res.append(d)
         return res
+
+    def set_option(self, name, value):
+        """Engine options (see pf_set_option in include/pf_b200.h), e.g. ``set_option("tcgen05", 1)``."""
+        eng = self._get_engine()
+        _native.check(eng.L.pf_set_option(eng.handle, name.encode(), int(value)))
+        self._options[name] = int(value)
 
     # ------------------------------------------------------------------------------------------ test hooks
     def debug_taps(self, enable=True):

@@ -55,7 +55,7 @@ def stream_ptr():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def conv_gemm(x_nhwc, w_oihw, bias, stride, pad, in_relu=False, act=0, res=None, res_relu=False):
+def conv_gemm(x_nhwc, w_oihw, bias, stride, pad, in_relu=False, act=0, res=None, res_relu=False, engine=0):
     """Run pf_op_conv_gemm.  x: [B,H,W,Cin] cuda fp32; w: [N,Cin,KH,KW] (cpu or cuda)."""
     from perspectivefields_b200 import _native
 
@@ -71,6 +71,6 @@ def conv_gemm(x_nhwc, w_oihw, bias, stride, pad, in_relu=False, act=0, res=None,
     r = res.contiguous() if res is not None else None
     _native.check(L.pf_op_conv_gemm(x_nhwc.contiguous().data_ptr(), B, H, W, Cin, hi.data_ptr(), lo.data_ptr(),
                                     b.data_ptr() if b is not None else None, N, KH, KW, stride, pad, int(in_relu), act,
-                                    r.data_ptr() if r is not None else None, int(res_relu), y.data_ptr(), stream_ptr()))
+                                    r.data_ptr() if r is not None else None, int(res_relu), y.data_ptr(), engine, stream_ptr()))
     torch.cuda.synchronize()
     return y

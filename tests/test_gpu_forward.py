@@ -38,7 +38,16 @@ def _check(out, ora, version, skip=()):
             assert tuple(o[k].shape) == tuple(v.shape) and o[k].dtype == torch.float32, k
             if k in skip:
                 continue
-            e = U.rel_err(o[k], v)
+            if k == "pred_latitude_original" and v.abs().max() > 75:
+                # degrees = asin(sin_lat): asin is not Lipschitz at +-1 (d/dx = 1/sqrt(1-x^2)), where the regression head
+                # clamps; compare in the sine domain everywhere and in degrees away from the poles.
+                a, b = o[k].detach().cpu().double(), v.double()
+                e = U.rel_err(torch.sin(torch.deg2rad(a)), torch.sin(torch.deg2rad(b)))
+                far = b.abs() < 75
+                if far.any():
+                    e = max(e, ((a - b).abs()[far].max() / b.abs().max()).item())
+            else:
+                e = U.rel_err(o[k], v)
             worst[k] = max(worst.get(k, 0.0), e)
             assert e < TOL, (version, k, e)
     return worst
@@ -167,3 +176,20 @@ def test_kernel_launches_are_counted():
     before = _native.lib().pf_kernel_launch_count()
     m.inference(wg.synth_images(1, 64, 64, 1)[0])
     assert _native.lib().pf_kernel_launch_count() - before > 300
+
+
+def test_tcgen05_engine_end_to_end():
+    """Same forward with the decoder-head convolutions routed to the tcgen05/TMEM kernel."""
+    version = "Paramnet-360Cities-edina-centered"
+    m, sd = model(version)
+    imgs = golden_images()
+    base = m.inference_batch(imgs)
+    m.set_option("tcgen05", 1)
+    try:
+        out = m.inference_batch(imgs)
+    finally:
+        m.set_option("tcgen05", 0)
+    print("tcgen05", _check(out, om.inference_batch(sd, version, imgs), version))
+    compare_with_golden(version, out, tol=TOL)
+    for a, b in zip(out, base):
+        assert U.rel_err(a["pred_latitude"], b["pred_latitude"]) < 1e-4

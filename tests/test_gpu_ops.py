@@ -127,3 +127,36 @@ def test_preprocess_is_bit_exact_vs_pillow(hw):
     torch.cuda.synchronize()
     got = y.cpu().numpy()
     assert np.array_equal(got[..., :3], ref) and not got[..., 3].any()
+
+
+# ---- tcgen05 / TMEM engine: same math, 128 x 256 tiles (N must be a multiple of 256 to be routed there)
+TC_CASES = [
+    (2, 20, 20, 256, 256, 3, 1, 1, 1, 1, 0, 0),     # RCU conv1
+    (1, 23, 17, 256, 256, 3, 1, 1, 0, 0, 1, 1),     # RCU conv2 + relu(residual), ragged M (391 rows)
+    (2, 16, 16, 64, 512, 3, 1, 1, 0, 0, 0, 0),      # composed proc conv (two N tiles)
+    (1, 1, 700, 320, 256, 1, 1, 0, 0, 0, 0, 0),     # plain linear, K = 320 (10 k-steps, ring wraps)
+    (1, 1, 64, 32, 256, 1, 1, 0, 0, 0, 0, 0),       # single k-step
+    (3, 40, 40, 256, 256, 3, 1, 1, 1, 0, 0, 0),     # 38 tiles, 72 k-steps
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_gemm_tcgen05(case):
+    B, H, W, Cin, N, K, s, p, ir, act, res, rr = case
+    g = torch.Generator().manual_seed(hash(case) & 0xFFFF)
+    x = _rn(g, B, Cin, H, W).cuda()
+    w = _rn(g, N, Cin, K, K) / (Cin * K * K) ** 0.5
+    b = _rn(g, N)
+    ref = F.conv2d((F.relu(x) if ir else x).double(), w.double().cuda(), b.double().cuda(), stride=s, padding=p)
+    ref = F.relu(ref) if act == 1 else (F.gelu(ref) if act == 2 else ref)
+    r = None
+    if res:
+        r = _rn(g, *ref.shape).cuda()
+        ref = ref + (F.relu(r) if rr else r).double()
+        r = r.permute(0, 2, 3, 1).contiguous()
+    xh = x.permute(0, 2, 3, 1).contiguous()
+    y = U.conv_gemm(xh, w, b, s, p, ir, act, r, rr, engine=1)
+    assert U.rel_err(y.permute(0, 3, 1, 2), ref) < 5e-5
+    # the two engines evaluate the same three bf16 products per term; only the fp32 summation order differs
+    y0 = U.conv_gemm(xh, w, b, s, p, ir, act, r, rr, engine=0)
+    assert U.rel_err(y, y0) < 2e-6
