@@ -97,8 +97,8 @@ int pf_forward(pf_handle h, const pf_batch* batch, void* workspace, int64_t work
 int pf_profile_enable(pf_handle h, int on);
 int pf_profile_read(pf_handle h, double* out12);
 
-/* Engine options.  "tcgen05" = 1 routes the convolutions whose output width is a multiple of 256 (the decoder heads'
- * 3x3 convolutions, ~55 % of the FLOPs) to the tcgen05/TMEM kernel instead of the warp-level HMMA kernel. */
+/* Engine options.  "tcgen05" (default 1): GEMM-shaped layers run on the tcgen05/TMEM kernel (conv_gemm_tc.cuh);
+ * 0 selects the warp-level HMMA kernel (conv_gemm.cuh) for every layer.  Both evaluate the same bf16x3 products. */
 int pf_set_option(pf_handle h, const char* name, int value);
 
 /* Debug taps (tests only): when enabled, intermediates of the next pf_forward are kept (never recycled) and can be

@@ -16,12 +16,19 @@
 
 namespace pf {
 
-constexpr int kTcBM = 128, kTcBN = 256, kTcBK = 32, kTcStages = 4;
+constexpr int kTcBM = 128, kTcBK = 32;
 constexpr int kTcABytes = kTcBM * 64;                       // one bf16 plane of the A tile (64 B rows)
-constexpr int kTcBBytes = kTcBN * 64;
-constexpr int kTcStageBytes = 2 * kTcABytes + 2 * kTcBBytes;  // 48 KB
-constexpr int kTcSmemBytes = kTcStages * kTcStageBytes + 256 + 1024;
 constexpr int kTcThreads = 160;
+// per-BN configuration: N tile, smem ring depth (BN=256: 4 x 48 KB, one CTA/SM; narrower tiles leave room for 2 CTAs/SM)
+template <int BN> struct TcCfg {
+  static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 3 : 4);
+  static constexpr int kBBytes = BN * 64;
+  static constexpr int kStageBytes = 2 * kTcABytes + 2 * kBBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 256 + 1024;
+  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  // Instruction descriptor: fp32 accumulate (bits 4-5 = 1), A/B = bf16 (bits 7-9, 10-12 = 1), both K-major, N >> 3 at 17, M >> 4 at 24.
+  static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+};
 
 // ------------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -79,10 +86,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
 }
-// Instruction descriptor: fp32 accumulate (bits 4-5 = 1), A/B = bf16 (bits 7-9, 10-12 = 1), both K-major, N >> 3 at 17, M >> 4 at 24.
-constexpr uint32_t kTcIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcBN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
-
+template <int BN>
 __global__ void __launch_bounds__(kTcThreads, 1) conv_gemm_tc_kernel(const ConvGemmParams p) {
+  constexpr int kTcBN = BN, kTcStages = TcCfg<BN>::kStages, kTcBBytes = TcCfg<BN>::kBBytes, kTcStageBytes = TcCfg<BN>::kStageBytes;
+  constexpr uint32_t kTcIdesc = TcCfg<BN>::kIdesc;
+  constexpr int kTmemCols = TcCfg<BN>::kTmemCols;
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t raw = smem_u32(smem_dyn);
   const uint32_t sbase = (raw + 1023u) & ~1023u;          // 1024 B aligned tile buffers
@@ -106,7 +114,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_gemm_tc_kernel(const ConvG
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, kTcBN);
+    tmem_alloc(tmem_slot, kTmemCols);
   }
   tc_fence_before();
   __syncthreads();
@@ -172,9 +180,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_gemm_tc_kernel(const ConvG
       const int k0 = kc * kTcBK;
       const uint32_t bhi = sbase + s * kTcStageBytes + 2 * kTcABytes;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
+      for (int i = 0; i < kTcBN / 16; ++i) {
         const int q = tid + 128 * i;            // [plane][n][chunk]
-        const int plane = q >> 10, n = (q & 1023) >> 2, c = q & 3;
+        const int plane = q / (kTcBN * 4), n = (q % (kTcBN * 4)) >> 2, c = q & 3;
         const bool ok = n0 + n < p.N;
         const __nv_bfloat16* src = (plane ? Wlo : Whi) + (long long)(ok ? n0 + n : 0) * p.K + k0 + c * 8;
         const uint32_t dst = bhi + plane * kTcBBytes + n * 64 + ((c ^ ((n >> 1) & 3)) << 4);
@@ -277,7 +285,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_gemm_tc_kernel(const ConvG
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, kTcBN);
+  if (warp == 4) tmem_dealloc(tmem, kTmemCols);
 }
 
 inline const char* conv_gemm_tc_check(const ConvGemmParams& p) {
@@ -291,19 +299,38 @@ inline const char* conv_gemm_tc_check(const ConvGemmParams& p) {
   return nullptr;
 }
 
-inline bool conv_gemm_tc_eligible(const ConvGemmParams& p) { return p.N % 256 == 0 && conv_gemm_tc_check(p) == nullptr; }
+// N tile for a problem (0 = not eligible for this engine)
+inline int conv_gemm_tc_bn(const ConvGemmParams& p) {
+  if (conv_gemm_tc_check(p) != nullptr) return 0;
+  if (p.N % 256 == 0) return 256;
+  if (p.N % 128 == 0) return 128;
+  if (p.N % 64 == 0) return 64;
+  return 32;
+}
+inline bool conv_gemm_tc_eligible(const ConvGemmParams& p) { return conv_gemm_tc_bn(p) != 0; }
 
-inline cudaError_t conv_gemm_tc_launch(const ConvGemmParams& p, cudaStream_t st) {
+template <int BN>
+inline cudaError_t conv_gemm_tc_launch_bn(const ConvGemmParams& p, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::kSmemBytes);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   const long long M = (long long)p.B * p.OH * p.OW;
-  dim3 grid((unsigned)cdivl(M, kTcBM), (unsigned)cdiv(p.N, kTcBN), (unsigned)p.groups);
-  conv_gemm_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(p);
+  dim3 grid((unsigned)cdivl(M, kTcBM), (unsigned)cdiv(p.N, BN), (unsigned)p.groups);
+  conv_gemm_tc_kernel<BN><<<grid, kTcThreads, TcCfg<BN>::kSmemBytes, st>>>(p);
   return cudaGetLastError();
+}
+
+inline cudaError_t conv_gemm_tc_launch(const ConvGemmParams& p, cudaStream_t st) {
+  switch (conv_gemm_tc_bn(p)) {
+    case 256: return conv_gemm_tc_launch_bn<256>(p, st);
+    case 128: return conv_gemm_tc_launch_bn<128>(p, st);
+    case 64: return conv_gemm_tc_launch_bn<64>(p, st);
+    case 32: return conv_gemm_tc_launch_bn<32>(p, st);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 }  // namespace pf

@@ -8,6 +8,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -107,9 +108,9 @@ struct pf_engine {
   struct DevTable { int ksize; int* bounds; int* coeffs; };
   std::map<int, DevTable> tables;
   // per-launch profiling of the GEMM engine (bench.py roofline leg): CUDA events on the launch stream
-  bool use_tc = false;   // route eligible convolutions (N % 256 == 0) to the tcgen05/TMEM engine
+  bool use_tc = true;    // route every eligible GEMM to the tcgen05/TMEM engine (option "tcgen05" = 0: HMMA engine)
   bool profile = false;
-  struct ProfRec { cudaEvent_t a, b; double flops; int cfg; };
+  struct ProfRec { cudaEvent_t a, b; double flops; int cfg; int M, N, K, KH, stride, groups, Cin; };
   std::vector<ProfRec> prof;
   // debug taps
   bool debug = false;
@@ -265,6 +266,7 @@ struct Fwd {
       CU(cudaEventCreate(&r.b));
       r.flops = 2.0 * (double)p.B * p.OH * p.OW * (double)p.N * (double)p.K * (double)p.groups;
       r.cfg = tc ? 3 : conv_gemm_config(p);
+      r.M = p.B * p.OH * p.OW; r.N = p.N; r.K = p.K; r.KH = p.KH; r.stride = p.stride; r.groups = p.groups; r.Cin = p.Cin;
       CU(cudaEventRecord(r.a, st));
       LAUNCHED(tc ? conv_gemm_tc_launch(p, st) : conv_gemm_launch(p, st));
       CU(cudaEventRecord(r.b, st));
@@ -671,16 +673,23 @@ int pf_set_option(pf_handle h, const char* name, int value) {
 int pf_profile_read(pf_handle h, double* out9) {
   if (!h || !out9) return fail(PF_ERR_ARG, "pf_profile_read: null argument");
   for (int i = 0; i < 12; ++i) out9[i] = 0.0;
+  FILE* csv = nullptr;
+  if (const char* path = getenv("PF_PROFILE_CSV")) {   // optional per-launch dump (profiles/)
+    csv = fopen(path, "w");
+    if (csv) fprintf(csv, "engine_cfg,M,N,K,Cin,KH,stride,groups,ms,algorithmic_tflops\n");
+  }
   for (auto& r : h->prof) {
     float ms = 0.f;
     CU(cudaEventSynchronize(r.b));
     CU(cudaEventElapsedTime(&ms, r.a, r.b));
+    if (csv) fprintf(csv, "%d,%d,%d,%d,%d,%d,%d,%d,%.4f,%.1f\n", r.cfg, r.M, r.N, r.K, r.Cin, r.KH, r.stride, r.groups, ms, r.flops / (ms * 1e9));
     out9[r.cfg * 3 + 0] += ms;
     out9[r.cfg * 3 + 1] += r.flops;
     out9[r.cfg * 3 + 2] += 1.0;
     cudaEventDestroy(r.a);
     cudaEventDestroy(r.b);
   }
+  if (csv) fclose(csv);
   h->prof.clear();
   return PF_OK;
 }

@@ -129,7 +129,7 @@ def test_preprocess_is_bit_exact_vs_pillow(hw):
     assert np.array_equal(got[..., :3], ref) and not got[..., 3].any()
 
 
-# ---- tcgen05 / TMEM engine: same math, 128 x 256 tiles (N must be a multiple of 256 to be routed there)
+# ---- tcgen05 / TMEM engine: same math, 128 x {256,128,64,32} tiles
 TC_CASES = [
     (2, 20, 20, 256, 256, 3, 1, 1, 1, 1, 0, 0),     # RCU conv1
     (1, 23, 17, 256, 256, 3, 1, 1, 0, 0, 1, 1),     # RCU conv2 + relu(residual), ragged M (391 rows)
@@ -137,6 +137,14 @@ TC_CASES = [
     (1, 1, 700, 320, 256, 1, 1, 0, 0, 0, 0, 0),     # plain linear, K = 320 (10 k-steps, ring wraps)
     (1, 1, 64, 32, 256, 1, 1, 0, 0, 0, 0, 0),       # single k-step
     (3, 40, 40, 256, 256, 3, 1, 1, 1, 0, 0, 0),     # 38 tiles, 72 k-steps
+    (1, 1, 700, 320, 640, 1, 1, 0, 0, 0, 0, 0),     # N tile 128 (kv linear)
+    (1, 1, 300, 96, 384, 1, 1, 0, 0, 2, 0, 0),      # N tile 128 + GELU
+    (1, 1, 130, 384, 96, 1, 1, 0, 0, 0, 1, 0),      # N tile 32 (x3) + residual
+    (2, 80, 80, 64, 64, 8, 8, 0, 0, 0, 0, 0),       # N tile 64, k = s = 8
+    (1, 24, 24, 64, 32, 3, 1, 1, 0, 1, 0, 0),       # N tile 32
+    (1, 40, 40, 320, 64, 3, 1, 1, 0, 1, 0, 0),      # N tile 64, K = 2880
+    (2, 40, 40, 64, 128, 3, 2, 1, 0, 0, 0, 0),      # N tile 128, stride 2
+    (1, 1, 500, 64, 320, 1, 1, 0, 0, 0, 0, 0),      # N = 320 -> five 64-wide tiles
 ]
 
 

@@ -8,7 +8,8 @@ g = torch.Generator().manual_seed(1)
 rn = lambda *s: torch.randn(*s, generator=g)
 cases = [(1, 1, 128, 32, 256, 1, 1, 0, 0, 0, 0, 0), (1, 1, 128, 64, 256, 1, 1, 0, 0, 0, 0, 0), (1, 1, 300, 320, 256, 1, 1, 0, 0, 0, 0, 0),
          (2, 20, 20, 256, 256, 3, 1, 1, 1, 1, 0, 0), (1, 23, 17, 256, 256, 3, 1, 1, 0, 0, 1, 1), (2, 16, 16, 64, 512, 3, 1, 1, 0, 0, 0, 0),
-         (3, 40, 40, 256, 256, 3, 1, 1, 1, 0, 0, 0)]
+         (3, 40, 40, 256, 256, 3, 1, 1, 1, 0, 0, 0), (1, 1, 700, 320, 640, 1, 1, 0, 0, 0, 0, 0), (1, 1, 130, 384, 96, 1, 1, 0, 0, 0, 1, 0),
+         (2, 80, 80, 64, 64, 8, 8, 0, 0, 0, 0, 0), (1, 24, 24, 64, 32, 3, 1, 1, 0, 1, 0, 0), (1, 1, 500, 64, 320, 1, 1, 0, 0, 0, 0, 0)]
 for (B, H, W, Cin, N, K, s, p, ir, act, res, rr) in cases:
     x = rn(B, Cin, H, W).cuda(); w = rn(N, Cin, K, K) / (Cin * K * K) ** 0.5; b = rn(N)
     ref = F.conv2d((F.relu(x) if ir else x).double(), w.double().cuda(), b.double().cuda(), stride=s, padding=p)
