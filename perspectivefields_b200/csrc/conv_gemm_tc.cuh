@@ -21,11 +21,11 @@ constexpr int kTcABytes = kTcBM * 64;                       // one bf16 plane of
 constexpr int kTcThreads = 160;
 // per-BN configuration: N tile, smem ring depth (BN=256: 4 x 48 KB, one CTA/SM; narrower tiles leave room for 2 CTAs/SM)
 template <int BN> struct TcCfg {
-  static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 3 : 4);
+  static constexpr int kStages = BN > 128 ? 4 : (BN > 64 ? 3 : 4);
   static constexpr int kBBytes = BN * 64;
   static constexpr int kStageBytes = 2 * kTcABytes + 2 * kBBytes;
   static constexpr int kSmemBytes = kStages * kStageBytes + 256 + 1024;
-  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  static constexpr int kTmemCols = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));  // power of two >= BN
   // Instruction descriptor: fp32 accumulate (bits 4-5 = 1), A/B = bf16 (bits 7-9, 10-12 = 1), both K-major, N >> 3 at 17, M >> 4 at 24.
   static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
 };
@@ -299,13 +299,12 @@ inline const char* conv_gemm_tc_check(const ConvGemmParams& p) {
   return nullptr;
 }
 
-// N tile for a problem (0 = not eligible for this engine)
+// N tile for a problem (0 = not eligible for this engine): the fewest tiles of at most 256 columns, then the narrowest
+// multiple of 32 that covers N with that many tiles (N = 320 -> 2 x 160, 640 -> 3 x 224, 384 -> 2 x 192, 96 -> 96).
 inline int conv_gemm_tc_bn(const ConvGemmParams& p) {
   if (conv_gemm_tc_check(p) != nullptr) return 0;
-  if (p.N % 256 == 0) return 256;
-  if (p.N % 128 == 0) return 128;
-  if (p.N % 64 == 0) return 64;
-  return 32;
+  const int tiles = cdiv(p.N, 256);
+  return cdiv(cdiv(p.N, tiles), 32) * 32;
 }
 inline bool conv_gemm_tc_eligible(const ConvGemmParams& p) { return conv_gemm_tc_bn(p) != 0; }
 
@@ -326,7 +325,11 @@ inline cudaError_t conv_gemm_tc_launch_bn(const ConvGemmParams& p, cudaStream_t 
 inline cudaError_t conv_gemm_tc_launch(const ConvGemmParams& p, cudaStream_t st) {
   switch (conv_gemm_tc_bn(p)) {
     case 256: return conv_gemm_tc_launch_bn<256>(p, st);
+    case 224: return conv_gemm_tc_launch_bn<224>(p, st);
+    case 192: return conv_gemm_tc_launch_bn<192>(p, st);
+    case 160: return conv_gemm_tc_launch_bn<160>(p, st);
     case 128: return conv_gemm_tc_launch_bn<128>(p, st);
+    case 96: return conv_gemm_tc_launch_bn<96>(p, st);
     case 64: return conv_gemm_tc_launch_bn<64>(p, st);
     case 32: return conv_gemm_tc_launch_bn<32>(p, st);
     default: return cudaErrorInvalidValue;

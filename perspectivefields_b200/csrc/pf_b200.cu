@@ -112,6 +112,7 @@ struct pf_engine {
   bool profile = false;
   struct ProfRec { cudaEvent_t a, b; double flops; int cfg; int M, N, K, KH, stride, groups, Cin; };
   std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> ev_pool;   // events are created once and recycled: no create/destroy inside a timed region
   // debug taps
   bool debug = false;
   std::vector<std::pair<std::string, std::pair<const float*, long long>>> taps;
@@ -262,8 +263,10 @@ struct Fwd {
     const bool tc = e->use_tc && conv_gemm_tc_eligible(p);
     if (e->profile) {
       pf_engine::ProfRec r{};
-      CU(cudaEventCreate(&r.a));
-      CU(cudaEventCreate(&r.b));
+      for (cudaEvent_t* ev : {&r.a, &r.b}) {
+        if (e->ev_pool.empty()) { CU(cudaEventCreate(ev)); }
+        else { *ev = e->ev_pool.back(); e->ev_pool.pop_back(); }
+      }
       r.flops = 2.0 * (double)p.B * p.OH * p.OW * (double)p.N * (double)p.K * (double)p.groups;
       r.cfg = tc ? 3 : conv_gemm_config(p);
       r.M = p.B * p.OH * p.OW; r.N = p.N; r.K = p.K; r.KH = p.KH; r.stride = p.stride; r.groups = p.groups; r.Cin = p.Cin;
@@ -604,6 +607,8 @@ int pf_destroy(pf_handle h) {
   if (!h) return PF_OK;
   cudaSetDevice(h->device);
   for (auto& kv : h->tables) { cudaFree(kv.second.bounds); cudaFree(kv.second.coeffs); }
+  for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto ev : h->ev_pool) cudaEventDestroy(ev);
   delete h;
   return PF_OK;
 }
@@ -686,8 +691,8 @@ int pf_profile_read(pf_handle h, double* out9) {
     out9[r.cfg * 3 + 0] += ms;
     out9[r.cfg * 3 + 1] += r.flops;
     out9[r.cfg * 3 + 2] += 1.0;
-    cudaEventDestroy(r.a);
-    cudaEventDestroy(r.b);
+    h->ev_pool.push_back(r.a);
+    h->ev_pool.push_back(r.b);
   }
   if (csv) fclose(csv);
   h->prof.clear();
