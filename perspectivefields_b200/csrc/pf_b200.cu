@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "conv_gemm.cuh"
 #include "conv_gemm_tc.cuh"
+#include "conv3x3_tc.cuh"
 #include "layers.cuh"
 #include "prepost.cuh"
 
@@ -108,6 +109,7 @@ struct pf_engine {
   struct DevTable { int ksize; int* bounds; int* coeffs; };
   std::map<int, DevTable> tables;
   // per-launch profiling of the GEMM engine (bench.py roofline leg): CUDA events on the launch stream
+  bool use_halo = true;  // 3x3/s1/p1 convolutions on the halo-tile tcgen05 kernel (option "halo3x3")
   bool use_tc = true;    // route every eligible GEMM to the tcgen05/TMEM engine (option "tcgen05" = 0: HMMA engine)
   bool profile = false;
   struct ProfRec { cudaEvent_t a, b; double flops; int cfg; int M, N, K, KH, stride, groups, Cin; };
@@ -261,6 +263,8 @@ struct Fwd {
     const char* msg = conv_gemm_check(p);
     if (msg) return fail(PF_ERR_ARG, "%s", msg);
     const bool tc = e->use_tc && conv_gemm_tc_eligible(p);
+    const bool halo = tc && e->use_halo && conv3x3_tc_eligible(p);
+    auto launch = [&]() { return halo ? conv3x3_tc_launch(p, st) : (tc ? conv_gemm_tc_launch(p, st) : conv_gemm_launch(p, st)); };
     if (e->profile) {
       pf_engine::ProfRec r{};
       for (cudaEvent_t* ev : {&r.a, &r.b}) {
@@ -268,15 +272,15 @@ struct Fwd {
         else { *ev = e->ev_pool.back(); e->ev_pool.pop_back(); }
       }
       r.flops = 2.0 * (double)p.B * p.OH * p.OW * (double)p.N * (double)p.K * (double)p.groups;
-      r.cfg = tc ? 3 : conv_gemm_config(p);
+      r.cfg = halo ? 4 : (tc ? 3 : conv_gemm_config(p));
       r.M = p.B * p.OH * p.OW; r.N = p.N; r.K = p.K; r.KH = p.KH; r.stride = p.stride; r.groups = p.groups; r.Cin = p.Cin;
       CU(cudaEventRecord(r.a, st));
-      LAUNCHED(tc ? conv_gemm_tc_launch(p, st) : conv_gemm_launch(p, st));
+      LAUNCHED(launch());
       CU(cudaEventRecord(r.b, st));
       e->prof.push_back(r);
       return PF_OK;
     }
-    LAUNCHED(tc ? conv_gemm_tc_launch(p, st) : conv_gemm_launch(p, st));
+    LAUNCHED(launch());
     return PF_OK;
   }
   static ConvGemmParams base(const float* A, int lda, int B, int H, int W, int Cin, int KH, int stride, int pad, const GemmW& w, int N,
@@ -666,18 +670,25 @@ int pf_forward(pf_handle h, const pf_batch* bt, void* workspace, int64_t workspa
 int pf_profile_enable(pf_handle h, int on) {
   if (!h) return fail(PF_ERR_ARG, "null handle");
   h->profile = on != 0;
+  // `on` > 1: pre-create the CUDA events for that many GEMM launches now, so none is created inside a timed region
+  while (on > 1 && (long long)h->ev_pool.size() < 2LL * on) {
+    cudaEvent_t ev;
+    CU(cudaEventCreate(&ev));
+    h->ev_pool.push_back(ev);
+  }
   return PF_OK;
 }
 int pf_set_option(pf_handle h, const char* name, int value) {
   if (!h || !name) return fail(PF_ERR_ARG, "pf_set_option: null argument");
   if (!strcmp(name, "tcgen05")) { h->use_tc = value != 0; return PF_OK; }
+  if (!strcmp(name, "halo3x3")) { h->use_halo = value != 0; return PF_OK; }
   return fail(PF_ERR_ARG, "pf_set_option: unknown option '%s'", name);
 }
-// out[cfg*3 + {0,1,2}] = {milliseconds, algorithmic FLOPs, launches} per GEMM engine configuration (4 configs),
+// out[cfg*3 + {0,1,2}] = {milliseconds, algorithmic FLOPs, launches} per GEMM engine configuration (5 configs),
 // accumulated since the last read; the caller must have synchronised the stream.
 int pf_profile_read(pf_handle h, double* out9) {
   if (!h || !out9) return fail(PF_ERR_ARG, "pf_profile_read: null argument");
-  for (int i = 0; i < 12; ++i) out9[i] = 0.0;
+  for (int i = 0; i < 15; ++i) out9[i] = 0.0;
   FILE* csv = nullptr;
   if (const char* path = getenv("PF_PROFILE_CSV")) {   // optional per-launch dump (profiles/)
     csv = fopen(path, "w");
@@ -735,6 +746,11 @@ int pf_op_conv_gemm(const float* x, int B, int H, int W, int Cin, const void* wh
   p.bias = bias; p.bias_mode = bias ? 1 : 0; p.act = act;
   p.res = res; p.ldr = N; p.res_relu = res_relu;
   p.C = y; p.ldc = N; p.groups = 1;
+  if (engine == 2) {
+    if (!conv3x3_tc_eligible(p)) return fail(PF_ERR_ARG, "pf_op_conv_gemm: shape not eligible for the halo-tile 3x3 kernel");
+    LAUNCHED(conv3x3_tc_launch(p, (cudaStream_t)stream));
+    return PF_OK;
+  }
   if (engine == 1) {
     const char* msg = conv_gemm_tc_check(p);
     if (msg) return fail(PF_ERR_ARG, "%s", msg);

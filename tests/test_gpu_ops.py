@@ -168,3 +168,35 @@ def test_conv_gemm_tcgen05(case):
     # the two engines evaluate the same three bf16 products per term; only the fp32 summation order differs
     y0 = U.conv_gemm(xh, w, b, s, p, ir, act, r, rr, engine=0)
     assert U.rel_err(y, y0) < 2e-6
+
+
+# ---- halo-tile tcgen05 kernel for 3x3 / stride 1 / pad 1 convolutions (16 x 8 pixel tiles, partial tiles masked)
+HALO_CASES = [
+    (2, 16, 8, 64, 32, 0, 1, 0, 0),       # exactly one tile per image, conv_fuse_conv1 shape class
+    (1, 80, 80, 256, 256, 1, 1, 0, 0),    # RCU conv1 at 80x80
+    (2, 23, 17, 256, 256, 0, 0, 1, 1),    # ragged tiles in both directions + relu(residual)
+    (1, 10, 10, 512, 512, 0, 0, 0, 0),    # proc conv at the coarsest level (tile larger than the image), two N tiles
+    (1, 40, 40, 320, 64, 0, 1, 0, 0),     # conv_fuse_conv0 shape class (5 chunks)
+    (3, 33, 9, 128, 128, 0, 0, 0, 0),
+]
+
+
+@pytest.mark.parametrize("case", HALO_CASES)
+def test_conv3x3_halo_tcgen05(case):
+    B, H, W, Cin, N, ir, act, res, rr = case
+    g = torch.Generator().manual_seed(hash(case) & 0xFFFF)
+    x = _rn(g, B, Cin, H, W).cuda()
+    w = _rn(g, N, Cin, 3, 3) / (Cin * 9) ** 0.5
+    b = _rn(g, N)
+    ref = F.conv2d((F.relu(x) if ir else x).double(), w.double().cuda(), b.double().cuda(), padding=1)
+    ref = F.relu(ref) if act == 1 else ref
+    r = None
+    if res:
+        r = _rn(g, *ref.shape).cuda()
+        ref = ref + (F.relu(r) if rr else r).double()
+        r = r.permute(0, 2, 3, 1).contiguous()
+    xh = x.permute(0, 2, 3, 1).contiguous()
+    y = U.conv_gemm(xh, w, b, 1, 1, ir, act, r, rr, engine=2)
+    assert U.rel_err(y.permute(0, 3, 1, 2), ref) < 5e-5
+    # same products, different fp32 summation order (channel chunks outermost instead of filter taps)
+    assert U.rel_err(y, U.conv_gemm(xh, w, b, 1, 1, ir, act, r, rr, engine=0)) < 2e-5
