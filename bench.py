@@ -191,7 +191,7 @@ def main():
     sampler.active = False
     ms = e0.elapsed_time(e1)
     launches = L.pf_kernel_launch_count() - launches0
-    prof = (ctypes.c_double * 15)()
+    prof = (ctypes.c_double * 21)()
     _native.check(L.pf_profile_read(eng.handle, prof))
     _native.check(L.pf_profile_enable(eng.handle, 0))
     clocks = sampler.stop()
@@ -241,10 +241,13 @@ def main():
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16, kernel timed inside a long step)" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
     cfg_names = ["conv_gemm_kernel<128,128> (HMMA)", "conv_gemm_kernel<128,64> (HMMA)", "conv_gemm_kernel<128,32> (HMMA)",
                  "conv_gemm_tc_kernel<BN> (tcgen05.mma kind::f16 + TMEM, bf16x3 split-precision implicit GEMM, 128 x BN tiles)",
-                 "conv3x3_tc_kernel<BN> (tcgen05.mma kind::f16 + TMEM, bf16x3 split precision, halo-tile 3x3 convolution, 16x8-pixel x BN tiles)"]
-    gemm_ms = sum(prof[3 * c] for c in range(5))
-    gemm_flops = sum(prof[3 * c + 1] for c in range(5))
-    dom = max(range(5), key=lambda c: prof[3 * c])
+                 "conv3x3_tc_kernel<BN> (tcgen05.mma kind::f16 + TMEM, bf16x3 split precision, halo-tile 3x3 convolution, 16x8-pixel x BN tiles)",
+                 "gemm_tma_kernel<BN,GEMM> (persistent TMA -> tcgen05.mma kind::f16 -> TMEM, bf16x3 split precision, 128 x BN x 32 tiles)",
+                 "gemm_tma_kernel<BN,HALO> (persistent TMA halo -> tcgen05.mma kind::f16 -> TMEM, bf16x3 split precision, 3x3 conv, 16x8-pixel x BN tiles)"]
+    NC = 7
+    gemm_ms = sum(prof[3 * c] for c in range(NC))
+    gemm_flops = sum(prof[3 * c + 1] for c in range(NC))
+    dom = max(range(NC), key=lambda c: prof[3 * c])
     dom_ms, dom_flops, dom_n = prof[3 * dom], prof[3 * dom + 1], prof[3 * dom + 2]
     achieved = dom_flops / (dom_ms / 1000.0) / 1e12 if dom_ms > 0 else None
     roofline = {
@@ -257,8 +260,8 @@ def main():
         "all_gemm_ms_per_step": gemm_ms / args.steps, "all_gemm_share_of_step": gemm_ms / ms if ms > 0 else None,
         "all_gemm_tflops": gemm_flops / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else None,
         "gflop_per_image_gemm": gemm_flops / (args.steps * B) / 1e9,
-        "per_engine": {cfg_names[c].split(" ")[0]: {"ms_per_step": prof[3 * c] / args.steps, "tflops": (prof[3 * c + 1] / (prof[3 * c] / 1000.0) / 1e12) if prof[3 * c] > 0 else None,
-                                                     "launches_per_step": prof[3 * c + 2] / args.steps} for c in range(5) if prof[3 * c + 2] > 0},
+        "per_engine": {cfg_names[c].split(" (")[0]: {"ms_per_step": prof[3 * c] / args.steps, "tflops": (prof[3 * c + 1] / (prof[3 * c] / 1000.0) / 1e12) if prof[3 * c] > 0 else None,
+                                                     "launches_per_step": prof[3 * c + 2] / args.steps} for c in range(NC) if prof[3 * c + 2] > 0},
     }
 
     # ---------------- CPU baseline: oracle port of the reference on the host cores (rank 0, N = 1 only) ---------

@@ -92,14 +92,16 @@ int64_t pf_workspace_bytes(pf_handle h, int n, int max_h);
 int pf_forward(pf_handle h, const pf_batch* batch, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Per-launch timing of the GEMM engine with CUDA events on the launch stream (bench.py roofline leg).  pf_profile_read
- * fills out15[cfg*3 + {0,1,2}] = {milliseconds, algorithmic FLOPs (2*M*N*K), launches} for the five engine configurations
- * (0: HMMA 128x128, 1: HMMA 128x64, 2: HMMA 128x32, 3: tcgen05 generic, 4: tcgen05 halo-tile 3x3) accumulated since the previous read; synchronise the stream first. */
+ * fills out21[cfg*3 + {0,1,2}] = {milliseconds, algorithmic FLOPs (2*M*N*K), launches} for the seven engine configurations
+ * (0-2: HMMA 128x{128,64,32}, 3: tcgen05 generic (register-staged A), 4: tcgen05 halo 3x3 (register-staged A),
+ *  5: TMA+tcgen05 GEMM, 6: TMA+tcgen05 halo 3x3) accumulated since the previous read; synchronise the stream first. */
 int pf_profile_enable(pf_handle h, int on /* 0 off, 1 on, n > 1: on + pre-create events for n GEMM launches */);
-int pf_profile_read(pf_handle h, double* out15);
+int pf_profile_read(pf_handle h, double* out21);
 
-/* Engine options.  "tcgen05" (default 1): GEMM-shaped layers run on the tcgen05/TMEM kernels; 0 selects the warp-level
- * HMMA kernel (conv_gemm.cuh) for every layer.  "halo3x3" (default 1): 3x3/stride-1 convolutions use the halo-tile
- * tcgen05 kernel (conv3x3_tc.cuh) instead of the generic im2col one.  All engines evaluate the same bf16x3 products. */
+/* Engine options.  "tma" (default 1): the forward graph runs on the persistent TMA -> tcgen05 -> TMEM engine with pre-split
+ * bf16 hi/lo activations (gemm_tma.cuh).  With "tma" = 0 the earlier engines are used (fp32 activations split on the fly):
+ * "tcgen05" (default 1) selects the register-staged tcgen05 kernels over the warp-level HMMA kernel, "halo3x3" (default 1)
+ * the halo-tile variant for 3x3/stride-1 convolutions.  All engines evaluate the same bf16x3 products. */
 int pf_set_option(pf_handle h, const char* name, int value);
 
 /* Debug taps (tests only): when enabled, intermediates of the next pf_forward are kept (never recycled) and can be
@@ -117,7 +119,7 @@ int pf_debug_copy(pf_handle h, const char* name, float* dst_dev, int64_t numel, 
  * y = act(conv(relu_in?(x)) + bias) (+ relu_res?(res));  act: 0 none, 1 ReLU, 2 GELU. */
 int pf_op_conv_gemm(const float* x, int B, int H, int W, int Cin, const void* whi, const void* wlo, const float* bias,
                     int N, int KH, int KW, int stride, int pad, int in_relu, int act, const float* res, int res_relu,
-                    float* y, int engine /* 0 = HMMA, 1 = tcgen05 generic, 2 = tcgen05 halo-tile 3x3 */, void* stream);
+                    float* y, int engine /* 0 = HMMA, 1 = tcgen05 generic, 2 = tcgen05 halo-tile 3x3, 3 = TMA engine */, void* stream);
 int pf_op_layernorm(const float* x, float* y, int64_t rows, int C, const float* w, const float* b, float eps, void* stream);
 int pf_op_attention(const float* q, const float* kv, float* out, int B, int N, int C, int heads, void* stream);
 int pf_op_dwconv3x3_gelu(const float* x, float* y, int B, int H, int W, int C, const float* w9c, const float* bias, void* stream);

@@ -23,6 +23,26 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uin
   lo = *reinterpret_cast<uint32_t*>(&l);
 }
 
+// A "split tensor": the two bf16 planes of an fp32 activation tensor, NHWC with `ld` channels per pixel.  GEMM inputs are
+// always stored this way by their producer so that the tcgen05 kernels can TMA-load them without any conversion.
+struct SplitT {
+  __nv_bfloat16* hi = nullptr;
+  __nv_bfloat16* lo = nullptr;
+  int ld = 0;
+};
+__device__ __forceinline__ void store_split4(__nv_bfloat16* hi, __nv_bfloat16* lo, long long idx, float4 v) {
+  uint2 h, l;
+  split_bf16x2(v.x, v.y, h.x, l.x);
+  split_bf16x2(v.z, v.w, h.y, l.y);
+  *reinterpret_cast<uint2*>(hi + idx) = h;
+  *reinterpret_cast<uint2*>(lo + idx) = l;
+}
+__device__ __forceinline__ void store_split1(__nv_bfloat16* hi, __nv_bfloat16* lo, long long idx, float v) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  hi[idx] = h;
+  lo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
 // ---------------------------------------------------------------- async copy / ldmatrix / mma wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

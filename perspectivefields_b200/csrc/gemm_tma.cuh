@@ -1,0 +1,336 @@
+// TMA -> tcgen05 -> TMEM engine: persistent, warp-specialised, epilogue overlapped with the next tile's main loop.
+//
+// All GEMM operands arrive PRE-SPLIT: activations as two bf16 planes (hi = bf16(x), lo = bf16(x - hi)) written by the
+// producing kernel's epilogue, weights as hi/lo planes split at load time.  Each product costs three bf16 MMAs
+// (lo*hi + hi*lo + hi*hi, fp32 accumulation in TMEM) -- see DESIGN.md "precision".  Nothing is converted here: tiles go
+// HBM/L2 --TMA--> swizzled shared memory --tcgen05.mma--> TMEM --tcgen05.ld--> fused epilogue --> HBM.
+//
+//   MODE_GEMM : C[M,N] = A[M,K] W[N,K]^T.     A tiles 128 x 32 (SWIZZLE_64B) by 2-D TMA, K step 32, NS-stage ring.
+//   MODE_HALO : 3x3 / stride 1 / pad 1 convolution, 16 x 8 pixel tiles.  One 4-D TMA per 64-channel chunk loads the
+//               18 x 10 input halo (OOB = zero padding) as [180 pixels][128 B] SWIZZLE_128B; the A operand of filter tap
+//               (ky,kx) is a shifted view of it (start + (ky*10+kx)*128 B, SBO = 1280 B; semantics probed by
+//               tools/tc_probe.cu).  Weights stream through an NS-stage ring of 32-wide K steps (2 per tap and chunk).
+//
+//   warp 0 : TMA producer (B ring; in MODE_GEMM also A)      warp 2 : TMEM allocator, MODE_HALO halo (A) producer
+//   warp 1 : MMA issuer (one elected lane)                   warps 4-7 : epilogue (TMEM lane quarter = warp % 4)
+//   two TMEM accumulators (2 x BN columns): the epilogue of tile i runs under the main loop of tile i+1.
+//
+// Epilogue (fused): + bias | border-class bias, ReLU / GELU, layer scale, + relu?(residual), + second residual; writes the
+// fp32 tensor and/or the bf16 hi/lo planes (optionally rectified) that the next GEMM will TMA-load.
+#pragma once
+#include <cuda.h>
+
+#include "conv_gemm_tc.cuh"
+
+namespace pf {
+
+constexpr int MODE_GEMM = 0, MODE_HALO = 1;
+constexpr int kTmaThreads = 256;
+constexpr int kHaloBytes = 180 * 128;   // one bf16 plane of an 18 x 10 pixel x 64 channel halo (what one TMA box delivers)
+
+struct TmaGemmParams {
+  int M;                    // MODE_GEMM: rows
+  int B, H, W;              // MODE_HALO: images, spatial size (output == input)
+  int Cin;                  // MODE_HALO: input channels per group (multiple of 64);  MODE_GEMM: K
+  int N, K;
+  int a_c0, a_gc;           // channel coordinate of the first input channel in A's tensor map, step per group
+  int c_split, a2_c0;       // MODE_HALO dual source: input channels >= c_split come from the A2 maps at a2_c0 + (ci - c_split); 0 = off
+  int groups;
+  // epilogue:  v = acc + bias;  v = act(v);  v *= gamma;  v += relu?(res);  v += res2
+  const float* bias; int bias_mode, bias_gstride;
+  int act; const float* gamma;
+  const float* res;  int ldr, r_coff, r_gcoff, res_relu;
+  const float* res2; int ldr2, r2_coff, r2_gcoff;
+  float* C; int ldc, c_coff, c_gcoff;                                           // fp32 output (may be null)
+  __nv_bfloat16* Shi; __nv_bfloat16* Slo; int lds, s_coff, s_gcoff, split_relu; // split output (may be null)
+};
+
+template <int BN, int MODE> struct TmaCfg {
+  static constexpr int kBPlane = BN * 64;                       // bf16 plane of a 32-wide K step of B
+  static constexpr int kAPlane = 128 * 64;                      // MODE_GEMM: plane of a 128 x 32 A tile
+  static constexpr int kStage = (MODE == MODE_GEMM ? 2 * kAPlane : 0) + 2 * kBPlane;
+  static constexpr int kABuf = 2 * kHtPlaneBytes;               // MODE_HALO: hi + lo halo planes (1024 B multiples)
+  static constexpr int kBudget = 225 * 1024 - (MODE == MODE_HALO ? 2 * kABuf : 0);
+  static constexpr int kStagesRaw = kBudget / kStage;
+  static constexpr int kStages = kStagesRaw > 16 ? 16 : kStagesRaw;
+  static constexpr int kSmemBytes = (MODE == MODE_HALO ? 2 * kABuf : 0) + kStages * kStage + 512 + 1024;
+  static constexpr int kTmemCols = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+  static constexpr uint32_t kIdesc = TcCfg<BN>::kIdesc;
+  static_assert(kStages >= 3, "ring too shallow");
+  static_assert(2 * BN <= 512, "two accumulators must fit TMEM");
+};
+
+// ------------------------------------------------------------------------------------------------ TMA PTX
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+struct TmaMaps {   // passed by value as a __grid_constant__ kernel parameter
+  CUtensorMap a_hi, a_lo, a2_hi, a2_lo, b_hi, b_lo;
+};
+
+template <int BN, int MODE>
+__global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_constant__ TmaMaps maps, const TmaGemmParams p, int tiles_x, int tiles_y) {
+  using Cfg = TmaCfg<BN, MODE>;
+  constexpr int NS = Cfg::kStages;
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t raw = smem_u32(smem_dyn);
+  const uint32_t sbase = (raw + 1023u) & ~1023u;
+  unsigned char* sm = smem_dyn + (sbase - raw);
+  const uint32_t a_base = sbase;                                                  // MODE_HALO: 2 halo buffers
+  const uint32_t ring = sbase + (MODE == MODE_HALO ? 2 * Cfg::kABuf : 0);         // NS stages
+  const uint32_t bars = ring + NS * Cfg::kStage;
+  auto full_b = [&](int s) { return bars + 8u * s; };
+  auto empty_b = [&](int s) { return bars + 8u * (NS + s); };
+  auto full_a = [&](int i) { return bars + 8u * (2 * NS + i); };
+  auto empty_a = [&](int i) { return bars + 8u * (2 * NS + 2 + i); };
+  auto tmem_full = [&](int i) { return bars + 8u * (2 * NS + 4 + i); };
+  auto tmem_empty = [&](int i) { return bars + 8u * (2 * NS + 6 + i); };
+  const uint32_t tmem_slot = bars + 8u * (2 * NS + 8);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_tiles = cdiv(p.N, BN);
+  const int m_tiles = MODE == MODE_GEMM ? cdiv(p.M, 128) : p.B * tiles_x * tiles_y;
+  const int total_tiles = m_tiles * n_tiles * p.groups;
+  const int nchunks = MODE == MODE_HALO ? p.Cin / 64 : 0;
+  const int nk = MODE == MODE_GEMM ? p.K / 32 : nchunks * 18;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.a_hi); tma_prefetch_desc(&maps.a_lo); tma_prefetch_desc(&maps.b_hi); tma_prefetch_desc(&maps.b_lo);
+    for (int s = 0; s < NS; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(full_a(i), 1); mbar_init(empty_a(i), 1); mbar_init(tmem_full(i), 1); mbar_init(tmem_empty(i), 128); }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + (tmem_slot - sbase));
+
+  // tile id -> (m tile, group, n tile); n fastest so that CTAs running together share the A tile / halo in L2
+  auto decode = [&](int tile, int& mt, int& g, int& n0) {
+    n0 = (tile % n_tiles) * BN;
+    tile /= n_tiles;
+    g = tile % p.groups;
+    mt = tile / p.groups;
+  };
+
+  if (warp == 0) {
+    // ======================================================================= TMA producer: B ring (+ A tiles in MODE_GEMM)
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int mt, g, n0;
+        decode(tile, mt, g, n0);
+        const int brow = g * p.N + n0;
+        for (int kc = 0; kc < nk; ++kc, ++it) {
+          const int s = it % NS;
+          mbar_wait(empty_b(s), ((it / NS) & 1) ^ 1);
+          mbar_expect_tx(full_b(s), Cfg::kStage);
+          const uint32_t st = ring + s * Cfg::kStage;
+          int kcol;
+          if (MODE == MODE_GEMM) {
+            kcol = kc * 32;
+            tma_load_2d(st, &maps.a_hi, full_b(s), p.a_c0 + g * p.a_gc + kcol, mt * 128);
+            tma_load_2d(st + Cfg::kAPlane, &maps.a_lo, full_b(s), p.a_c0 + g * p.a_gc + kcol, mt * 128);
+          } else {
+            const int c = kc / 18, u = kc - c * 18;
+            kcol = (u >> 1) * p.Cin + c * 64 + (u & 1) * 32;
+          }
+          const uint32_t bdst = st + (MODE == MODE_GEMM ? 2 * Cfg::kAPlane : 0);
+          tma_load_2d(bdst, &maps.b_hi, full_b(s), kcol, brow);
+          tma_load_2d(bdst + Cfg::kBPlane, &maps.b_lo, full_b(s), kcol, brow);
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ======================================================================= MODE_HALO: halo (A) producer
+    if (MODE == MODE_HALO && lane == 0) {
+      int ita = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int mt, g, n0;
+        decode(tile, mt, g, n0);
+        const int tx = mt % tiles_x, ty = (mt / tiles_x) % tiles_y, bimg = mt / (tiles_x * tiles_y);
+        for (int c = 0; c < nchunks; ++c, ++ita) {
+          const int buf = ita & 1;
+          mbar_wait(empty_a(buf), ((ita >> 1) & 1) ^ 1);
+          mbar_expect_tx(full_a(buf), 2 * kHaloBytes);
+          const uint32_t dst = a_base + buf * Cfg::kABuf;
+          const int ci = c * 64;
+          if (p.c_split > 0 && ci >= p.c_split) {
+            tma_load_4d(dst, &maps.a2_hi, full_a(buf), p.a2_c0 + ci - p.c_split, tx * kHtTileW - 1, ty * kHtTileH - 1, bimg);
+            tma_load_4d(dst + kHtPlaneBytes, &maps.a2_lo, full_a(buf), p.a2_c0 + ci - p.c_split, tx * kHtTileW - 1, ty * kHtTileH - 1, bimg);
+          } else {
+            tma_load_4d(dst, &maps.a_hi, full_a(buf), p.a_c0 + g * p.a_gc + ci, tx * kHtTileW - 1, ty * kHtTileH - 1, bimg);
+            tma_load_4d(dst + kHtPlaneBytes, &maps.a_lo, full_a(buf), p.a_c0 + g * p.a_gc + ci, tx * kHtTileW - 1, ty * kHtTileH - 1, bimg);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================================================================= MMA issuer
+    int it = 0, ita = 0, tl = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+      const int as = tl & 1;
+      mbar_wait(tmem_empty(as), ((tl >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t acc = tmem + (uint32_t)(as * BN);
+      for (int kc = 0; kc < nk; ++kc, ++it) {
+        const int s = it % NS;
+        uint32_t a_hi, a_lo;
+        int a_kbase = 0;
+        bool chunk_end = false;
+        if (MODE == MODE_HALO) {
+          const int c = kc / 18, u = kc - c * 18;
+          const int tap = u >> 1, ky = tap / 3, kx = tap - ky * 3;
+          const int buf = ita & 1;
+          if (u == 0) mbar_wait(full_a(buf), (ita >> 1) & 1);
+          a_hi = a_base + buf * Cfg::kABuf + (ky * kHtHaloW + kx) * 128;
+          a_lo = a_hi + kHtPlaneBytes;
+          a_kbase = (u & 1) * 64;                         // second half of the 128 B pixel row
+          chunk_end = u == 17;
+        } else {
+          a_hi = ring + s * Cfg::kStage;
+          a_lo = a_hi + Cfg::kAPlane;
+        }
+        mbar_wait(full_b(s), (it / NS) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t b_hi = ring + s * Cfg::kStage + (MODE == MODE_GEMM ? 2 * Cfg::kAPlane : 0), b_lo = b_hi + Cfg::kBPlane;
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            uint64_t dah, dal;
+            if (MODE == MODE_HALO) { dah = ht_a_desc(a_hi + a_kbase + kk * 32); dal = ht_a_desc(a_lo + a_kbase + kk * 32); }
+            else { dah = tc_smem_desc(a_hi + kk * 32); dal = tc_smem_desc(a_lo + kk * 32); }
+            const uint64_t dbh = tc_smem_desc(b_hi + kk * 32), dbl = tc_smem_desc(b_lo + kk * 32);
+            umma_bf16(acc, dal, dbh, Cfg::kIdesc, (kc | kk) ? 1u : 0u);
+            umma_bf16(acc, dah, dbl, Cfg::kIdesc, 1u);
+            umma_bf16(acc, dah, dbh, Cfg::kIdesc, 1u);
+          }
+          umma_commit(empty_b(s));
+          if (MODE == MODE_HALO && chunk_end) umma_commit(empty_a(ita & 1));
+          if (kc == nk - 1) umma_commit(tmem_full(as));
+        }
+        __syncwarp();
+        if (MODE == MODE_HALO && chunk_end) ++ita;
+      }
+    }
+  } else if (warp >= 4) {
+    // ======================================================================= epilogue warps
+    const int q = warp - 4;                       // TMEM lane quarter
+    const int r = q * 32 + lane;                  // row of the tile
+    int tl = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+      int mt, g, n0;
+      decode(tile, mt, g, n0);
+      const int as = tl & 1;
+      long long m;
+      bool valid;
+      int cls_off = 0;
+      if (MODE == MODE_GEMM) {
+        m = (long long)mt * 128 + r;
+        valid = m < p.M;
+      } else {
+        const int tx = mt % tiles_x, ty = (mt / tiles_x) % tiles_y, bimg = mt / (tiles_x * tiles_y);
+        const int oy = ty * kHtTileH + (r >> 3), ox = tx * kHtTileW + (r & 7);
+        valid = oy < p.H && ox < p.W;
+        m = ((long long)bimg * p.H + oy) * p.W + ox;
+        if (p.bias_mode == 2) {
+          const int ry = oy == 0 ? 0 : (oy == p.H - 1 ? 2 : 1);
+          const int rx = ox == 0 ? 0 : (ox == p.W - 1 ? 2 : 1);
+          cls_off = (ry * 3 + rx) * p.N;
+        }
+      }
+      const float* __restrict__ bias = p.bias ? p.bias + (long long)g * p.bias_gstride : nullptr;
+      mbar_wait(tmem_full(as), (tl >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + ch * 32), v);
+        const int nb = n0 + ch * 32;
+        if (valid && nb < p.N) {
+          float o[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]);
+          if (p.bias_mode) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + cls_off + nb + j));
+              o[j] += bv.x; o[j + 1] += bv.y; o[j + 2] += bv.z; o[j + 3] += bv.w;
+            }
+          }
+          if (p.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], 0.f);
+          } else if (p.act == 2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = gelu_erf(o[j]);
+          }
+          if (p.gamma) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 gv = __ldg(reinterpret_cast<const float4*>(p.gamma + nb + j));
+              o[j] *= gv.x; o[j + 1] *= gv.y; o[j + 2] *= gv.z; o[j + 3] *= gv.w;
+            }
+          }
+          if (p.res) {
+            const float* rp = p.res + m * p.ldr + p.r_coff + g * p.r_gcoff + nb;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 rv = *reinterpret_cast<const float4*>(rp + j);
+              if (p.res_relu) { rv.x = fmaxf(rv.x, 0.f); rv.y = fmaxf(rv.y, 0.f); rv.z = fmaxf(rv.z, 0.f); rv.w = fmaxf(rv.w, 0.f); }
+              o[j] += rv.x; o[j + 1] += rv.y; o[j + 2] += rv.z; o[j + 3] += rv.w;
+            }
+          }
+          if (p.res2) {
+            const float* rp = p.res2 + m * p.ldr2 + p.r2_coff + g * p.r2_gcoff + nb;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 rv = *reinterpret_cast<const float4*>(rp + j);
+              o[j] += rv.x; o[j + 1] += rv.y; o[j + 2] += rv.z; o[j + 3] += rv.w;
+            }
+          }
+          if (p.C) {
+            float* cp = p.C + m * p.ldc + p.c_coff + g * p.c_gcoff + nb;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+          }
+          if (p.Shi) {
+            const long long so = m * p.lds + p.s_coff + g * p.s_gcoff + nb;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 h, l;
+              float t[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) t[e] = p.split_relu ? fmaxf(o[j + e], 0.f) : o[j + e];
+              split_bf16x2(t[0], t[1], h.x, l.x); split_bf16x2(t[2], t[3], h.y, l.y);
+              split_bf16x2(t[4], t[5], h.z, l.z); split_bf16x2(t[6], t[7], h.w, l.w);
+              *reinterpret_cast<uint4*>(p.Shi + so + j) = h;
+              *reinterpret_cast<uint4*>(p.Slo + so + j) = l;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tmem_empty(as));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, Cfg::kTmemCols);
+}
+
+}  // namespace pf

@@ -15,7 +15,8 @@ namespace pf {
 template <int KH, int KW, int STRIDE, int PAD, int COUT, int PPT, int PGROUPS>
 __global__ void __launch_bounds__(COUT* PGROUPS) stem_conv_kernel(const float* __restrict__ in, int ldin, int B, int H, int W,
                                                                   const float* __restrict__ w, const float* __restrict__ bias,
-                                                                  float* __restrict__ out, int OH, int OW, int relu) {
+                                                                  float* __restrict__ out, int OH, int OW, int relu,
+                                                                  __nv_bfloat16* __restrict__ shi, __nv_bfloat16* __restrict__ slo) {
   constexpr int PIX = PPT * PGROUPS;                   // output pixels per block (along x)
   constexpr int IN_W = (PIX - 1) * STRIDE + KW;        // input columns needed
   __shared__ float s_in[KH][IN_W][3];
@@ -56,18 +57,20 @@ __global__ void __launch_bounds__(COUT* PGROUPS) stem_conv_kernel(const float* _
     if (ox < OW) {
       float v = acc[j];
       if (relu) v = fmaxf(v, 0.f);
-      out[((long long)(b * OH + oy) * OW + ox) * COUT + co] = v;
+      const long long oi = ((long long)(b * OH + oy) * OW + ox) * COUT + co;
+      if (out) out[oi] = v;
+      if (shi) store_split1(shi, slo, oi, v);
     }
   }
 }
 
 template <int KH, int KW, int STRIDE, int PAD, int COUT>
 inline cudaError_t stem_conv_launch(const float* in, int ldin, int B, int H, int W, const float* w, const float* bias,
-                                    float* out, int relu, cudaStream_t st) {
+                                    float* out, int relu, cudaStream_t st, SplitT sp = SplitT()) {
   constexpr int PPT = 4, PGROUPS = (COUT == 64) ? 4 : 2;
   const int OH = (H + 2 * PAD - KH) / STRIDE + 1, OW = (W + 2 * PAD - KW) / STRIDE + 1;
   const int tiles_x = cdiv(OW, PPT * PGROUPS);
-  stem_conv_kernel<KH, KW, STRIDE, PAD, COUT, PPT, PGROUPS><<<B * OH * tiles_x, COUT * PGROUPS, 0, st>>>(in, ldin, B, H, W, w, bias, out, OH, OW, relu);
+  stem_conv_kernel<KH, KW, STRIDE, PAD, COUT, PPT, PGROUPS><<<B * OH * tiles_x, COUT * PGROUPS, 0, st>>>(in, ldin, B, H, W, w, bias, out, OH, OW, relu, sp.hi, sp.lo);
   return cudaGetLastError();
 }
 
@@ -77,7 +80,8 @@ inline cudaError_t stem_conv_launch(const float* in, int ldin, int B, int H, int
 // in NHWC).  One warp per row; two-pass (mean, then centred variance) in registers.
 template <int MAXPER>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ in, float* __restrict__ out, long long rows, int C,
-                                                        const float* __restrict__ gw, const float* __restrict__ gb, float eps) {
+                                                        const float* __restrict__ gw, const float* __restrict__ gb, float eps,
+                                                        __nv_bfloat16* __restrict__ shi, __nv_bfloat16* __restrict__ slo) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -99,20 +103,23 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     q = fmaf(d, d, q);
   }
   const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
-  float* y = out + row * C;
 #pragma unroll
   for (int i = 0; i < MAXPER; ++i) {
     const int c = lane + 32 * i;
-    if (c < C) y[c] = (v[i] - mean) * rstd * __ldg(gw + c) + __ldg(gb + c);
+    if (c < C) {
+      const float y = (v[i] - mean) * rstd * __ldg(gw + c) + __ldg(gb + c);
+      if (out) out[row * C + c] = y;
+      if (shi) store_split1(shi, slo, row * C + c, y);
+    }
   }
 }
 
 inline cudaError_t layernorm_launch(const float* in, float* out, long long rows, int C, const float* w, const float* b, float eps,
-                                    cudaStream_t st) {
+                                    cudaStream_t st, SplitT sp = SplitT()) {
   const unsigned grid = (unsigned)cdivl(rows, 8);
-  if (C <= 128) layernorm_kernel<4><<<grid, 256, 0, st>>>(in, out, rows, C, w, b, eps);
-  else if (C <= 384) layernorm_kernel<12><<<grid, 256, 0, st>>>(in, out, rows, C, w, b, eps);
-  else if (C <= 768) layernorm_kernel<24><<<grid, 256, 0, st>>>(in, out, rows, C, w, b, eps);
+  if (C <= 128) layernorm_kernel<4><<<grid, 256, 0, st>>>(in, out, rows, C, w, b, eps, sp.hi, sp.lo);
+  else if (C <= 384) layernorm_kernel<12><<<grid, 256, 0, st>>>(in, out, rows, C, w, b, eps, sp.hi, sp.lo);
+  else if (C <= 768) layernorm_kernel<24><<<grid, 256, 0, st>>>(in, out, rows, C, w, b, eps, sp.hi, sp.lo);
   else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
@@ -125,7 +132,7 @@ inline cudaError_t layernorm_launch(const float* in, float* out, long long rows,
 // two passes over the keys (max, then exp/accumulate) -- fp32 CUDA-core math, exact softmax.
 constexpr int kAttnNkv = 100, kAttnD = 64, kAttnQ = 128;
 __global__ void __launch_bounds__(kAttnQ) attention_kernel(const float* __restrict__ q, const float* __restrict__ kv, float* __restrict__ out,
-                                                           int N, int C, float scale) {
+                                                           int N, int C, float scale, __nv_bfloat16* __restrict__ shi, __nv_bfloat16* __restrict__ slo) {
   extern __shared__ __align__(16) float s_kv[];  // K[100][64], V[100][64]
   float* sK = s_kv;
   float* sV = s_kv + kAttnNkv * kAttnD;
@@ -182,13 +189,16 @@ __global__ void __launch_bounds__(kAttnQ) attention_kernel(const float* __restri
     }
   }
   const float inv = 1.0f / l;
-  float* op = out + ((long long)b * N + n) * C + h * kAttnD;
+  const long long oi = ((long long)b * N + n) * C + h * kAttnD;
 #pragma unroll
-  for (int d = 0; d < kAttnD; d += 4)
-    *reinterpret_cast<float4*>(op + d) = make_float4(o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv);
+  for (int d = 0; d < kAttnD; d += 4) {
+    const float4 r = make_float4(o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv);
+    if (out) *reinterpret_cast<float4*>(out + oi + d) = r;
+    if (shi) store_split4(shi, slo, oi + d, r);
+  }
 }
 
-inline cudaError_t attention_launch(const float* q, const float* kv, float* out, int B, int N, int C, int heads, cudaStream_t st) {
+inline cudaError_t attention_launch(const float* q, const float* kv, float* out, int B, int N, int C, int heads, cudaStream_t st, SplitT sp = SplitT()) {
   constexpr int smem = 2 * kAttnNkv * kAttnD * 4;
   static bool configured = false;
   if (!configured) {
@@ -197,7 +207,7 @@ inline cudaError_t attention_launch(const float* q, const float* kv, float* out,
     configured = true;
   }
   dim3 grid(cdiv(N, kAttnQ), heads, B);
-  attention_kernel<<<grid, kAttnQ, smem, st>>>(q, kv, out, N, C, 0.125f);
+  attention_kernel<<<grid, kAttnQ, smem, st>>>(q, kv, out, N, C, 0.125f, sp.hi, sp.lo);
   return cudaGetLastError();
 }
 
@@ -205,7 +215,8 @@ inline cudaError_t attention_launch(const float* q, const float* kv, float* out,
 // Depthwise 3x3 conv (pad 1) + bias + GELU(erf) on NHWC -- Mix-FFN middle, mix_transformers.py:51-52,502-508.
 // w: [9][C], thread = 4 channels of one pixel.
 __global__ void __launch_bounds__(256) dwconv3x3_gelu_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C,
-                                                             const float* __restrict__ w, const float* __restrict__ bias) {
+                                                             const float* __restrict__ w, const float* __restrict__ bias,
+                                                             __nv_bfloat16* __restrict__ shi = nullptr, __nv_bfloat16* __restrict__ slo = nullptr) {
   const int C4 = C >> 2;
   const long long total = (long long)B * H * W * C4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -227,7 +238,9 @@ __global__ void __launch_bounds__(256) dwconv3x3_gelu_kernel(const float* __rest
         acc.x = fmaf(v.x, k.x, acc.x); acc.y = fmaf(v.y, k.y, acc.y); acc.z = fmaf(v.z, k.z, acc.z); acc.w = fmaf(v.w, k.w, acc.w);
       }
     }
-    reinterpret_cast<float4*>(out)[i] = make_float4(gelu_erf(acc.x), gelu_erf(acc.y), gelu_erf(acc.z), gelu_erf(acc.w));
+    const float4 r = make_float4(gelu_erf(acc.x), gelu_erf(acc.y), gelu_erf(acc.z), gelu_erf(acc.w));
+    if (out) reinterpret_cast<float4*>(out)[i] = r;
+    if (shi) store_split4(shi, slo, i * 4, r);
   }
 }
 
@@ -269,7 +282,7 @@ inline unsigned ew_grid(long long total) {
 // edges clamped.  ATen: src = 0.5*(dst+0.5)-0.5 clamped at 0, i1 = min(i0+1, in-1).  NHWC, float4 per thread.
 // `in` channel pitch/offset (ldi, icoff) select one head's half of a 512-channel tensor.
 __global__ void __launch_bounds__(256) upsample2x_kernel(const float* __restrict__ in, int ldi, int icoff, float* __restrict__ out, int ldo, int ocoff,
-                                                         int B, int H, int W, int C) {
+                                                         int B, int H, int W, int C, __nv_bfloat16* __restrict__ shi = nullptr, __nv_bfloat16* __restrict__ slo = nullptr) {
   const int C4 = C >> 2, OH = 2 * H, OW = 2 * W;
   const long long total = (long long)B * OH * OW * C4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -291,8 +304,49 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const float* __restrict
     r.y = hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y);
     r.z = hy * (hx * v00.z + lx * v01.z) + ly * (hx * v10.z + lx * v11.z);
     r.w = hy * (hx * v00.w + lx * v01.w) + ly * (hx * v10.w + lx * v11.w);
-    *reinterpret_cast<float4*>(out + ((long long)(b * OH + y) * OW + x) * ldo + ocoff + c4 * 4) = r;
+    const long long oi = ((long long)(b * OH + y) * OW + x) * ldo + ocoff + c4 * 4;
+    if (out) *reinterpret_cast<float4*>(out + oi) = r;
+    if (shi) store_split4(shi, slo, oi, r);
   }
+}
+
+// =====================================================================================================
+// Patch gather on split planes: dst[m][(ky,kx,c)] = src[b, oy*stride - pad + ky, ox*stride - pad + kx, c] (zero outside),
+// for the few strided convolutions (overlap patch embed 3x3/2, spatial-reduction k = s = R, ConvNeXt downsample 2x2/2)
+// so that they run on the same TMA GEMM kernel.  16 B (8 channels) per thread per plane.
+__global__ void __launch_bounds__(256) im2col_split_kernel(const __nv_bfloat16* __restrict__ shi, const __nv_bfloat16* __restrict__ slo, int lds,
+                                                           __nv_bfloat16* __restrict__ dhi, __nv_bfloat16* __restrict__ dlo,
+                                                           int B, int H, int W, int C, int OH, int OW, int KH, int stride, int pad) {
+  const int C8 = C >> 3;
+  const long long total = (long long)B * OH * OW * KH * KH * C8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % C8);
+    long long r = i / C8;
+    const int kx = (int)(r % KH); r /= KH;
+    const int ky = (int)(r % KH); r /= KH;
+    const int ox = (int)(r % OW); r /= OW;
+    const int oy = (int)(r % OH); const int b = (int)(r / OH);
+    const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
+    uint4 h = make_uint4(0, 0, 0, 0), l = h;
+    if ((unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W) {
+      const long long si = ((long long)(b * H + iy) * W + ix) * lds + c8 * 8;
+      h = __ldg(reinterpret_cast<const uint4*>(shi + si));
+      l = __ldg(reinterpret_cast<const uint4*>(slo + si));
+    }
+    reinterpret_cast<uint4*>(dhi)[i] = h;
+    reinterpret_cast<uint4*>(dlo)[i] = l;
+  }
+}
+
+// fp32 = hi + lo (debug taps / tests)
+__global__ void __launch_bounds__(256) merge_split_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, float* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __bfloat162float(hi[i]) + __bfloat162float(lo[i]);
+}
+// fp32 -> split planes (tests)
+__global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long n, int relu) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) store_split1(hi, lo, i, relu ? fmaxf(in[i], 0.f) : in[i]);
 }
 
 // =====================================================================================================

@@ -19,6 +19,7 @@
 #include "conv_gemm.cuh"
 #include "conv_gemm_tc.cuh"
 #include "conv3x3_tc.cuh"
+#include "tma_host.cuh"
 #include "layers.cuh"
 #include "prepost.cuh"
 
@@ -109,6 +110,8 @@ struct pf_engine {
   struct DevTable { int ksize; int* bounds; int* coeffs; };
   std::map<int, DevTable> tables;
   // per-launch profiling of the GEMM engine (bench.py roofline leg): CUDA events on the launch stream
+  bool use_tma = true;   // whole forward on the TMA -> tcgen05 engine with pre-split activations (option "tma"; 0 = legacy engines)
+  int sm_count = 148;
   bool use_halo = true;  // 3x3/s1/p1 convolutions on the halo-tile tcgen05 kernel (option "halo3x3")
   bool use_tc = true;    // route every eligible GEMM to the tcgen05/TMEM engine (option "tcgen05" = 0: HMMA engine)
   bool profile = false;
@@ -301,6 +304,121 @@ struct Fwd {
     p.act = act; p.res = res; p.ldr = N; p.gamma = gamma;
     return gemm(p);
   }
+
+  // ------------------------------------------------------------------------------------------ TMA engine helpers
+  SplitT salloc(long long pixels, int ld) {
+    SplitT t;
+    t.hi = (__nv_bfloat16*)ar.alloc(pixels * ld * 2);
+    t.lo = (__nv_bfloat16*)ar.alloc(pixels * ld * 2);
+    t.ld = ld;
+    return t;
+  }
+  int tap_split(const char* name, const SplitT& t, long long numel) {
+    if (!e->debug) return PF_OK;
+    float* cp = ar.f(numel);
+    if (dry) return PF_OK;
+    LAUNCHED((merge_split_kernel<<<(unsigned)cdivl(numel, 256), 256, 0, st>>>(t.hi, t.lo, cp, numel), cudaGetLastError()));
+    e->taps.push_back({name, {cp, numel}});
+    return PF_OK;
+  }
+  int launch_tma(int mode, const TmaMaps& maps, const TmaGemmParams& p) {
+    const int bn = tma_pick_bn(p.N, mode);
+    if (e->profile) {
+      pf_engine::ProfRec r{};
+      for (cudaEvent_t* ev : {&r.a, &r.b}) {
+        if (e->ev_pool.empty()) { CU(cudaEventCreate(ev)); }
+        else { *ev = e->ev_pool.back(); e->ev_pool.pop_back(); }
+      }
+      const double Mrows = mode == MODE_GEMM ? (double)p.M : (double)p.B * p.H * p.W;
+      r.flops = 2.0 * Mrows * (double)p.N * (double)p.K * (double)p.groups;
+      r.cfg = mode == MODE_GEMM ? 5 : 6;
+      r.M = (int)Mrows; r.N = p.N; r.K = p.K; r.KH = mode == MODE_GEMM ? 1 : 3; r.stride = 1; r.groups = p.groups; r.Cin = p.Cin;
+      CU(cudaEventRecord(r.a, st));
+      LAUNCHED(gemm_tma_launch(mode, maps, p, bn, e->sm_count, st));
+      CU(cudaEventRecord(r.b, st));
+      e->prof.push_back(r);
+      return PF_OK;
+    }
+    LAUNCHED(gemm_tma_launch(mode, maps, p, bn, e->sm_count, st));
+    return PF_OK;
+  }
+  struct Epi {   // epilogue options of one TMA GEMM / conv
+    float* C = nullptr; int ldc = 0, c_coff = 0, c_gcoff = 0;
+    SplitT S; int s_coff = 0, s_gcoff = 0, split_relu = 0;
+    int act = 0; const float* gamma = nullptr;
+    const float* res = nullptr; int ldr = 0, r_coff = 0, r_gcoff = 0, res_relu = 0;
+    const float* res2 = nullptr; int ldr2 = 0, r2_coff = 0, r2_gcoff = 0;
+    int bias_mode = 1;
+  };
+  static void fill_epi(TmaGemmParams& p, const GemmW& w, const Epi& o, int bias_gstride) {
+    p.bias = w.b; p.bias_mode = w.b ? o.bias_mode : 0; p.bias_gstride = bias_gstride;
+    p.act = o.act; p.gamma = o.gamma;
+    p.res = o.res; p.ldr = o.ldr; p.r_coff = o.r_coff; p.r_gcoff = o.r_gcoff; p.res_relu = o.res_relu;
+    p.res2 = o.res2; p.ldr2 = o.ldr2; p.r2_coff = o.r2_coff; p.r2_gcoff = o.r2_gcoff;
+    p.C = o.C; p.ldc = o.ldc; p.c_coff = o.c_coff; p.c_gcoff = o.c_gcoff;
+    p.Shi = o.S.hi; p.Slo = o.S.lo; p.lds = o.S.ld; p.s_coff = o.s_coff; p.s_gcoff = o.s_gcoff; p.split_relu = o.split_relu;
+  }
+  // C[M, N] = A[M, K] W^T : A = split planes with row pitch A.ld, first channel a_c0
+  int tgemm(const SplitT& A, long long M, int K, int a_c0, const GemmW& w, int N, const Epi& o) {
+    if (dry) return PF_OK;
+    if (K % 32 || N % 32 || A.ld % 8) return fail(PF_ERR_ARG, "tgemm: K/N must be multiples of 32");
+    TmaGemmParams p{};
+    p.M = (int)M; p.Cin = K; p.N = N; p.K = K; p.a_c0 = a_c0; p.groups = 1;
+    fill_epi(p, w, o, 0);
+    TmaMaps maps{};
+    const int bn = tma_pick_bn(N, MODE_GEMM);
+    const char* msg = nullptr;
+    if (!msg) msg = tma_map_2d(&maps.a_hi, A.hi, A.ld, M, A.ld, 128);
+    if (!msg) msg = tma_map_2d(&maps.a_lo, A.lo, A.ld, M, A.ld, 128);
+    if (!msg) msg = tma_map_2d(&maps.b_hi, w.hi, K, N, K, bn);
+    if (!msg) msg = tma_map_2d(&maps.b_lo, w.lo, K, N, K, bn);
+    if (msg) return fail(PF_ERR_CUDA, "%s", msg);
+    maps.a2_hi = maps.a_hi; maps.a2_lo = maps.a_lo;
+    return launch_tma(MODE_GEMM, maps, p);
+  }
+  // 3x3 / stride 1 / pad 1 convolution on split NHWC planes (optionally a second source for channels >= c_split)
+  int thalo(const SplitT& A, int a_c0, int a_gc, const SplitT* A2, int c_split, int a2_c0, int B, int H, int W, int Cin, const GemmW& w, int N,
+            int groups, int bias_gstride, const Epi& o) {
+    if (dry) return PF_OK;
+    if (Cin % 64 || N % 32 || (A2 && c_split % 64)) return fail(PF_ERR_ARG, "thalo: Cin must be a multiple of 64, N of 32");
+    TmaGemmParams p{};
+    p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.N = N; p.K = 9 * Cin; p.a_c0 = a_c0; p.a_gc = a_gc; p.groups = groups;
+    p.c_split = A2 ? c_split : 0; p.a2_c0 = a2_c0;
+    fill_epi(p, w, o, bias_gstride);
+    TmaMaps maps{};
+    const int bn = tma_pick_bn(N, MODE_HALO);
+    const char* msg = nullptr;
+    if (!msg) msg = tma_map_halo(&maps.a_hi, A.hi, B, H, W, A.ld);
+    if (!msg) msg = tma_map_halo(&maps.a_lo, A.lo, B, H, W, A.ld);
+    if (A2) {
+      if (!msg) msg = tma_map_halo(&maps.a2_hi, A2->hi, B, H, W, A2->ld);
+      if (!msg) msg = tma_map_halo(&maps.a2_lo, A2->lo, B, H, W, A2->ld);
+    } else { maps.a2_hi = maps.a_hi; maps.a2_lo = maps.a_lo; }
+    if (!msg) msg = tma_map_2d(&maps.b_hi, w.hi, p.K, (long long)groups * N, p.K, bn);
+    if (!msg) msg = tma_map_2d(&maps.b_lo, w.lo, p.K, (long long)groups * N, p.K, bn);
+    if (msg) return fail(PF_ERR_CUDA, "%s", msg);
+    return launch_tma(MODE_HALO, maps, p);
+  }
+  // strided / patchifying convolution = patch gather on split planes + TMA GEMM
+  int tconv_gather(const SplitT& A, int B, int H, int W, int Cin, int KH, int stride, int pad, const GemmW& w, int N, const Epi& o) {
+    const int OH = (H + 2 * pad - KH) / stride + 1, OW = (W + 2 * pad - KH) / stride + 1;
+    const long long M = (long long)B * OH * OW;
+    const int K = KH * KH * Cin;
+    const long long m = ar.mark();
+    SplitT col = salloc(M, K);
+    if (!dry) {
+      if (Cin % 8) return fail(PF_ERR_ARG, "tconv_gather: Cin %% 8");
+      LAUNCHED((im2col_split_kernel<<<ew_grid(M * K / 8), 256, 0, st>>>(A.hi, A.lo, A.ld, col.hi, col.lo, B, H, W, Cin, OH, OW, KH, stride, pad), cudaGetLastError()));
+    }
+    int r = tgemm(col, M, K, 0, w, N, o);
+    ar.release(m);
+    return r;
+  }
+  int ln_split(const float* x, const SplitT& y, long long rows, int C, const LnW& w, float eps, float* yf = nullptr) {
+    if (dry) return PF_OK;
+    LAUNCHED(layernorm_launch(x, yf, rows, C, w.w, w.b, eps, st, y));
+    return PF_OK;
+  }
   int ln(const float* x, float* y, long long rows, int C, const LnW& w, float eps) {
     if (dry) return PF_OK;
     LAUNCHED(layernorm_launch(x, y, rows, C, w.w, w.b, eps, st));
@@ -332,18 +450,19 @@ static int pre_rows_needed(int H) {  // input rows one block of kPreRows output 
 }
 constexpr int kPreMaxSmemRows = 200 * 1024 / (kNet * 3);
 
-static int run_forward(Fwd& F, const pf_batch* bt, int max_h_for_dry) {
+// ----------------------------------------------------------------------------------------------- shared graph sections
+// uint8 HWC (any size) or pre-resized fp32 CHW -> x0 [n,320,320,4] fp32 normalised
+static int fwd_preprocess(Fwd& F, const pf_batch* bt, float*& x0, PreImage*& d_pre, PostImage*& d_post) {
   pf_engine* e = F.e;
   const pf_model_desc& D = e->desc;
   const int n = F.n;
   const bool dry = F.dry;
   cudaStream_t st = F.st;
   Arena& ar = F.ar;
-
   // ---------------- pre-process: uint8 HWC (any size) -> [n,320,320,4] fp32 normalised -------------------
-  float* x0 = ar.f((long long)n * kNet * kNet * 4);
-  PreImage* d_pre = (PreImage*)ar.alloc((long long)n * sizeof(PreImage));
-  PostImage* d_post = (PostImage*)ar.alloc((long long)n * sizeof(PostImage));
+  x0 = ar.f((long long)n * kNet * kNet * 4);
+  d_pre = (PreImage*)ar.alloc((long long)n * sizeof(PreImage));
+  d_post = (PostImage*)ar.alloc((long long)n * sizeof(PostImage));
   if (!dry) {
     if (bt->images_u8) {
       std::vector<PreImage> pre(n);
@@ -377,6 +496,67 @@ static int run_forward(Fwd& F, const pf_batch* bt, int max_h_for_dry) {
                 cudaGetLastError()));
     }
   }
+  return PF_OK;
+}
+
+// prediction 1x1 convs (+ normalise / clamp) -> NCHW outputs, then argmax decode (classification) and resample to the
+// original resolutions.  conv1_out: [n,320,320,64] fp32 (gravity head channels 0-31, latitude head 32-63).
+static int fwd_tails_post(Fwd& F, const pf_batch* bt, const float* conv1_out, PostImage* d_post) {
+  pf_engine* e = F.e;
+  const pf_model_desc& D = e->desc;
+  const int n = F.n;
+  const bool dry = F.dry;
+  cudaStream_t st = F.st;
+  Arena& ar = F.ar;
+  // prediction tails -> NCHW outputs (returned to the caller)
+  const int HW = kNet * kNet;
+  if (!dry) {
+    const unsigned grid = (unsigned)cdivl((long long)n * HW, 128);
+    LAUNCHED((pred_tail_kernel<<<grid, 128, D.gravity_classes * 33 * 4, st>>>(conv1_out, 64, 0, e->pred_g_w, e->pred_g_b, bt->pred_gravity, n, HW,
+                                                                           D.gravity_classes, D.gravity_classes == 2 ? 1 : 0), cudaGetLastError()));
+    LAUNCHED((pred_tail_kernel<<<grid, 128, D.latitude_classes * 33 * 4, st>>>(conv1_out, 64, 32, e->pred_l_w, e->pred_l_b, bt->pred_latitude, n, HW,
+                                                                            D.latitude_classes, D.latitude_classes == 1 ? 2 : 0), cudaGetLastError()));
+  }
+
+  // ---------------- post-process to the original resolutions ------------------------------------------------
+  const float* vec = dry ? nullptr : bt->pred_gravity;
+  const float* lat = dry ? nullptr : bt->pred_latitude;
+  const bool cls_g = D.gravity_classes != 2, cls_l = D.latitude_classes != 1;
+  if (cls_g) {
+    float* dv = ar.f((long long)n * 2 * HW);
+    if (!dry) LAUNCHED((argmax_decode_kernel<<<(unsigned)cdivl((long long)n * HW, 256), 256, 0, st>>>(bt->pred_gravity, dv, n, HW, D.gravity_classes, 1), cudaGetLastError()));
+    vec = dv;
+  }
+  if (cls_l) {
+    float* dl = ar.f((long long)n * HW);
+    if (!dry) LAUNCHED((argmax_decode_kernel<<<(unsigned)cdivl((long long)n * HW, 256), 256, 0, st>>>(bt->pred_latitude, dl, n, HW, D.latitude_classes, 0), cudaGetLastError()));
+    lat = dl;
+  }
+  if (!dry) {
+    std::vector<PostImage> post(n);
+    long long total = 0;
+    for (int i = 0; i < n; ++i) {
+      post[i] = PostImage{bt->height[i], bt->width[i], bt->gravity_original_offset[i], bt->latitude_original_offset[i], total};
+      total += (long long)bt->height[i] * bt->width[i];
+    }
+    CU(cudaMemcpyAsync(d_post, post.data(), n * sizeof(PostImage), cudaMemcpyHostToDevice, st));
+    LAUNCHED((postprocess_kernel<<<(unsigned)cdivl(total, 256), 256, 0, st>>>(vec, lat, d_post, n, total, bt->gravity_original, bt->latitude_original,
+                                                                             cls_l ? 0 : 1), cudaGetLastError()));
+  }
+
+  return PF_OK;
+}
+
+static int run_forward(Fwd& F, const pf_batch* bt, int max_h_for_dry) {
+  pf_engine* e = F.e;
+  const pf_model_desc& D = e->desc;
+  const int n = F.n;
+  const bool dry = F.dry;
+  cudaStream_t st = F.st;
+  Arena& ar = F.ar;
+
+  float* x0; PreImage* d_pre; PostImage* d_post;
+  TRY(fwd_preprocess(F, bt, x0, d_pre, d_post));
   F.tap("pre", x0, (long long)n * kNet * kNet * 4);
 
   // ---------------- persistent feature maps ---------------------------------------------------------------
@@ -500,41 +680,10 @@ static int run_forward(Fwd& F, const pf_batch* bt, int max_h_for_dry) {
     }
     ar.release(m);
   }
-  // prediction tails -> NCHW outputs (returned to the caller)
+  TRY(fwd_tails_post(F, bt, conv1_out, d_post));
   const int HW = kNet * kNet;
-  if (!dry) {
-    const unsigned grid = (unsigned)cdivl((long long)n * HW, 128);
-    LAUNCHED((pred_tail_kernel<<<grid, 128, D.gravity_classes * 33 * 4, st>>>(conv1_out, 64, 0, e->pred_g_w, e->pred_g_b, bt->pred_gravity, n, HW,
-                                                                           D.gravity_classes, D.gravity_classes == 2 ? 1 : 0), cudaGetLastError()));
-    LAUNCHED((pred_tail_kernel<<<grid, 128, D.latitude_classes * 33 * 4, st>>>(conv1_out, 64, 32, e->pred_l_w, e->pred_l_b, bt->pred_latitude, n, HW,
-                                                                            D.latitude_classes, D.latitude_classes == 1 ? 2 : 0), cudaGetLastError()));
-  }
-
-  // ---------------- post-process to the original resolutions ------------------------------------------------
-  const float* vec = dry ? nullptr : bt->pred_gravity;
-  const float* lat = dry ? nullptr : bt->pred_latitude;
   const bool cls_g = D.gravity_classes != 2, cls_l = D.latitude_classes != 1;
-  if (cls_g) {
-    float* dv = ar.f((long long)n * 2 * HW);
-    if (!dry) LAUNCHED((argmax_decode_kernel<<<(unsigned)cdivl((long long)n * HW, 256), 256, 0, st>>>(bt->pred_gravity, dv, n, HW, D.gravity_classes, 1), cudaGetLastError()));
-    vec = dv;
-  }
-  if (cls_l) {
-    float* dl = ar.f((long long)n * HW);
-    if (!dry) LAUNCHED((argmax_decode_kernel<<<(unsigned)cdivl((long long)n * HW, 256), 256, 0, st>>>(bt->pred_latitude, dl, n, HW, D.latitude_classes, 0), cudaGetLastError()));
-    lat = dl;
-  }
-  if (!dry) {
-    std::vector<PostImage> post(n);
-    long long total = 0;
-    for (int i = 0; i < n; ++i) {
-      post[i] = PostImage{bt->height[i], bt->width[i], bt->gravity_original_offset[i], bt->latitude_original_offset[i], total};
-      total += (long long)bt->height[i] * bt->width[i];
-    }
-    CU(cudaMemcpyAsync(d_post, post.data(), n * sizeof(PostImage), cudaMemcpyHostToDevice, st));
-    LAUNCHED((postprocess_kernel<<<(unsigned)cdivl(total, 256), 256, 0, st>>>(vec, lat, d_post, n, total, bt->gravity_original, bt->latitude_original,
-                                                                             cls_l ? 0 : 1), cudaGetLastError()));
-  }
+  (void)HW;
 
   // ---------------- ParamNet (ConvNeXt-T on the predicted fields) -------------------------------------------
   if (D.param_net != PF_PARAM_NONE) {
@@ -579,6 +728,183 @@ static int run_forward(Fwd& F, const pf_batch* bt, int max_h_for_dry) {
   return PF_OK;
 }
 
+
+// =============================================================================================== TMA forward graph
+// Same network as run_forward, on the TMA -> tcgen05 engine: every GEMM input is a pre-split bf16 hi/lo tensor written by
+// its producer (LayerNorm, attention, depthwise conv, upsample, stem, or the previous GEMM's epilogue).
+static int run_forward_tma(Fwd& F, const pf_batch* bt) {
+  pf_engine* e = F.e;
+  const pf_model_desc& D = e->desc;
+  const int n = F.n;
+  const bool dry = F.dry;
+  cudaStream_t st = F.st;
+  Arena& ar = F.ar;
+  using Epi = Fwd::Epi;
+
+  float* x0; PreImage* d_pre; PostImage* d_post;
+  TRY(fwd_preprocess(F, bt, x0, d_pre, d_post));
+  F.tap("pre", x0, (long long)n * kNet * kNet * 4);
+
+  SplitT cfeat[4];
+  for (int s = 0; s < 4; ++s) cfeat[s] = F.salloc((long long)n * kMitRes[s] * kMitRes[s], kMitDims[s]);
+  SplitT ll = F.salloc((long long)n * 160 * 160, 64);
+  if (!dry) LAUNCHED((stem_conv_launch<7, 7, 2, 3, 64>(x0, 4, n, kNet, kNet, e->llenc_w, e->llenc_b, nullptr, 1, st, ll)));
+  TRY(F.tap_split("ll", ll, (long long)n * 160 * 160 * 64));
+
+  // ---------------- MiT-B3 encoder ---------------------------------------------------------------------------
+  for (int s = 0; s < 4; ++s) {
+    const int C = kMitDims[s], R = kMitRes[s], N = R * R, heads = kMitHeads[s], sr = kMitSr[s];
+    const long long rows = (long long)n * N;
+    const long long m = ar.mark();
+    float* x = ar.f(rows * C);
+    float* tf = ar.f(rows * C);                      // patch-embed conv output (before its LayerNorm)
+    SplitT t1 = F.salloc(rows, C);                   // LayerNorm output (GEMM input only)
+    float* q = ar.f(rows * C);
+    SplitT a = F.salloc(rows, C);                    // attention output
+    float* t2f = ar.f((long long)n * 100 * C);
+    SplitT t2 = F.salloc((long long)n * 100, C);
+    float* kv = ar.f((long long)n * 100 * 2 * C);
+    float* h1 = ar.f(rows * 4 * C);
+    SplitT h2 = F.salloc(rows, 4 * C);
+    if (s == 0) {
+      if (!dry) LAUNCHED((stem_conv_launch<7, 7, 4, 3, 64>(x0, 4, n, kNet, kNet, e->embed1_w, e->embed1_b, tf, 0, st)));
+    } else {
+      Epi o; o.C = tf; o.ldc = C;
+      TRY(F.tconv_gather(cfeat[s - 1], n, kMitRes[s - 1], kMitRes[s - 1], kMitDims[s - 1], 3, 2, 1, e->embed[s], C, o));
+    }
+    TRY(F.ln(tf, x, rows, C, e->embed_ln[s], 1e-5f));
+    F.tapf(x, rows * C, "mit.s%d.embed", s + 1);
+    for (int i = 0; i < kMitDepths[s]; ++i) {
+      const MitBlockW& b = e->blocks[s][i];
+      TRY(F.ln_split(x, t1, rows, C, b.ln1, 1e-6f));
+      { Epi o; o.C = q; o.ldc = C; TRY(F.tgemm(t1, rows, C, 0, b.q, C, o)); }
+      if (sr > 1) {
+        { Epi o; o.C = t2f; o.ldc = C; TRY(F.tconv_gather(t1, n, R, R, C, sr, sr, 0, b.sr, C, o)); }
+        TRY(F.ln_split(t2f, t2, (long long)n * 100, C, b.srln, 1e-5f));
+        { Epi o; o.C = kv; o.ldc = 2 * C; TRY(F.tgemm(t2, (long long)n * 100, C, 0, b.kv, 2 * C, o)); }
+      } else {
+        Epi o; o.C = kv; o.ldc = 2 * C;
+        TRY(F.tgemm(t1, rows, C, 0, b.kv, 2 * C, o));
+      }
+      if (!dry) LAUNCHED(attention_launch(q, kv, nullptr, n, N, C, heads, st, a));
+      { Epi o; o.C = x; o.ldc = C; o.res = x; o.ldr = C; TRY(F.tgemm(a, rows, C, 0, b.proj, C, o)); }
+      F.tapf(x, rows * C, "mit.s%d.b%d.attn", s + 1, i);
+      TRY(F.ln_split(x, t1, rows, C, b.ln2, 1e-6f));
+      { Epi o; o.C = h1; o.ldc = 4 * C; TRY(F.tgemm(t1, rows, C, 0, b.fc1, 4 * C, o)); }
+      if (!dry) LAUNCHED((dwconv3x3_gelu_kernel<<<ew_grid(rows * C), 256, 0, st>>>(h1, nullptr, n, R, R, 4 * C, b.dw_w, b.dw_b, h2.hi, h2.lo), cudaGetLastError()));
+      { Epi o; o.C = x; o.ldc = C; o.res = x; o.ldr = C; TRY(F.tgemm(h2, rows, 4 * C, 0, b.fc2, C, o)); }
+      F.tapf(x, rows * C, "mit.s%d.b%d", s + 1, i);
+    }
+    TRY(F.ln_split(x, cfeat[s], rows, C, e->stage_norm[s], 1e-6f));
+    { char nm[32]; snprintf(nm, sizeof nm, "mit.c%d", s + 1); TRY(F.tap_split(nm, cfeat[s], rows * C)); }
+    ar.release(m);
+  }
+
+  // ---------------- decoder heads (group 0 = gravity, group 1 = latitude, side by side in the channel dimension) ----
+  float* conv1_out = ar.f((long long)n * kNet * kNet * 64);
+  {
+    const long long m = ar.mark();
+    float* fused = nullptr;       // fp32 top-down feature of the previous level, upsampled to this level's resolution
+    SplitT fused_s;               // level 1 only: the final fused feature at 160x160, split (input of conv_fuse_conv0)
+    for (int lvl = 4; lvl >= 1; --lvl) {
+      const int r = kMitRes[lvl - 1], Cin = kMitDims[lvl - 1];
+      const long long px = (long long)n * r * r;
+      float* t = ar.f(px * 512);
+      SplitT rt = F.salloc(px, 512);        // relu(t)
+      SplitT u = F.salloc(px, 512);         // rectified conv1 outputs
+      float* v = ar.f(px * 512);
+      SplitT rv = F.salloc(px, 512);        // relu(v)
+      float* w2 = ar.f(px * 512);
+      {   // composed linear_c{lvl} o linear_c{lvl}_proc (both heads: N = 512), border-class bias
+        Epi o; o.C = t; o.ldc = 512; o.S = rt; o.split_relu = 1; o.bias_mode = 2;
+        TRY(F.thalo(cfeat[lvl - 1], 0, 0, nullptr, 0, 0, n, r, r, Cin, e->proc[lvl - 1], 512, 1, 0, o));
+        F.tapf(t, px * 512, "head.proc%d", lvl);
+      }
+      auto rcu = [&](const SplitT& A, const GemmW& w, Epi o) {
+        o.c_gcoff = 256; o.s_gcoff = 256; o.r_gcoff = 256; o.r2_gcoff = 256;
+        return F.thalo(A, 0, 256, nullptr, 0, 0, n, r, r, 256, w, 256, 2, 256, o);
+      };
+      const float* of = t;
+      const SplitT* os = &rt;
+      if (lvl < 4) {
+        { Epi o; o.S = u; o.act = 1; TRY(rcu(rt, e->rcu[lvl - 1][0][0], o)); }
+        { Epi o; o.C = v; o.ldc = 512; o.S = rv; o.split_relu = 1; o.res = t; o.ldr = 512; o.res_relu = 1; o.res2 = fused; o.ldr2 = 512;
+          TRY(rcu(u, e->rcu[lvl - 1][0][1], o)); }
+        of = v; os = &rv;
+      }
+      { Epi o; o.S = u; o.act = 1; TRY(rcu(*os, e->rcu[lvl - 1][1][0], o)); }
+      { Epi o; o.C = w2; o.ldc = 512; o.res = of; o.ldr = 512; o.res_relu = 1; TRY(rcu(u, e->rcu[lvl - 1][1][1], o)); }
+      if (lvl > 1) {
+        float* up = ar.f(px * 4 * 512);
+        if (!dry) LAUNCHED((upsample2x_kernel<<<ew_grid(px * 4 * 128), 256, 0, st>>>(w2, 512, 0, up, 512, 0, n, r, r, 512), cudaGetLastError()));
+        fused = up;
+        F.tapf(up, px * 4 * 512, "head.fusion%d", lvl);
+      } else {
+        fused_s = F.salloc(px * 4, 512);
+        if (!dry) LAUNCHED((upsample2x_kernel<<<ew_grid(px * 4 * 128), 256, 0, st>>>(w2, 512, 0, nullptr, 512, 0, n, r, r, 512, fused_s.hi, fused_s.lo), cudaGetLastError()));
+        TRY(F.tap_split("head.fusion1", fused_s, px * 4 * 512));
+      }
+    }
+    // conv_fuse_conv0 on cat([fused, ll]) -> ReLU ; x2 ; conv_fuse_conv1 -> ReLU
+    float* c0 = ar.f((long long)n * 160 * 160 * 128);
+    {
+      Epi o; o.C = c0; o.ldc = 128; o.c_gcoff = 64; o.act = 1;
+      TRY(F.thalo(fused_s, 0, 256, &ll, 256, 0, n, 160, 160, 320, e->conv0, 64, 2, 64, o));
+      F.tap("head.conv0", c0, (long long)n * 160 * 160 * 128);
+    }
+    SplitT c0u = F.salloc((long long)n * kNet * kNet, 128);
+    if (!dry) LAUNCHED((upsample2x_kernel<<<ew_grid((long long)n * kNet * kNet * 32), 256, 0, st>>>(c0, 128, 0, nullptr, 128, 0, n, 160, 160, 128, c0u.hi, c0u.lo), cudaGetLastError()));
+    {
+      Epi o; o.C = conv1_out; o.ldc = 64; o.c_gcoff = 32; o.act = 1;
+      TRY(F.thalo(c0u, 0, 64, nullptr, 0, 0, n, kNet, kNet, 64, e->conv1, 32, 2, 32, o));
+      F.tap("head.conv1", conv1_out, (long long)n * kNet * kNet * 64);
+    }
+    ar.release(m);
+  }
+  TRY(fwd_tails_post(F, bt, conv1_out, d_post));
+
+  // ---------------- ParamNet (ConvNeXt-T on the predicted fields) -------------------------------------------
+  if (D.param_net != PF_PARAM_NONE) {
+    if (D.gravity_classes != 2 || D.latitude_classes != 1) return fail(PF_ERR_ARG, "ParamNet needs regression heads");
+    const int S = D.param_net == PF_PARAM_CENTERED ? kNet : D.param_input_size;
+    float* pin = ar.f((long long)n * S * S * 4);
+    if (!dry) LAUNCHED((pack_fields_kernel<<<(unsigned)cdivl((long long)n * S * S, 256), 256, 0, st>>>(bt->pred_gravity, bt->pred_latitude, pin, n, S), cudaGetLastError()));
+    int r = S / 4;
+    float* x = ar.f((long long)n * r * r * 96);
+    if (!dry) LAUNCHED((stem_conv_launch<4, 4, 4, 0, 96>(pin, 4, n, S, S, e->pn_stem_w, e->pn_stem_b, x, 0, st)));
+    TRY(F.ln(x, x, (long long)n * r * r, 96, e->pn_stem_ln, 1e-6f));
+    for (int s = 0; s < 4; ++s) {
+      const int C = kCnxDims[s];
+      if (s > 0) {
+        const int r2 = r / 2;
+        SplitT y = F.salloc((long long)n * r * r, kCnxDims[s - 1]);
+        TRY(F.ln_split(x, y, (long long)n * r * r, kCnxDims[s - 1], e->pn_ds_ln[s], 1e-6f));
+        float* xn = ar.f((long long)n * r2 * r2 * C);
+        Epi o; o.C = xn; o.ldc = C;
+        TRY(F.tconv_gather(y, n, r, r, kCnxDims[s - 1], 2, 2, 0, e->pn_ds[s], C, o));
+        x = xn; r = r2;
+      }
+      const long long rows = (long long)n * r * r;
+      float* yf = ar.f(rows * C);
+      SplitT y = F.salloc(rows, C);
+      SplitT h = F.salloc(rows, 4 * C);
+      for (int j = 0; j < kCnxDepths[s]; ++j) {
+        const CnxBlockW& b = e->pn_blocks[s][j];
+        if (!dry) LAUNCHED((dwconv7x7_kernel<<<ew_grid(rows * C / 4), 256, 0, st>>>(x, yf, n, r, r, C, b.dw_w, b.dw_b), cudaGetLastError()));
+        TRY(F.ln_split(yf, y, rows, C, b.ln, 1e-6f));
+        { Epi o; o.S = h; o.act = 2; TRY(F.tgemm(y, rows, C, 0, b.pw1, 4 * C, o)); }
+        { Epi o; o.C = x; o.ldc = C; o.res = x; o.ldr = C; o.gamma = b.gamma; TRY(F.tgemm(h, rows, 4 * C, 0, b.pw2, C, o)); }
+      }
+      F.tapf(x, rows * C, "cnx.s%d", s);
+    }
+    if (!dry) {
+      if (!bt->params) return fail(PF_ERR_ARG, "params output is NULL");
+      LAUNCHED((param_tail_kernel<<<n, 256, 0, st>>>(x, r * r, e->pn_norm.w, e->pn_norm.b, e->pn_head_w, e->pn_head_b, bt->params, D.param_net), cudaGetLastError()));
+    }
+  }
+  return PF_OK;
+}
+
 // ----------------------------------------------------------------------------------------------- C ABI
 extern "C" {
 
@@ -602,6 +928,7 @@ int pf_create(int device, const pf_model_desc* desc, pf_handle* out) {
   if (prop.major != 10) return fail(PF_ERR_CUDA, "pf_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
   pf_engine* e = new pf_engine();
   e->device = device;
+  e->sm_count = prop.multiProcessorCount;
   e->desc = *desc;
   *out = e;
   return PF_OK;
@@ -637,7 +964,7 @@ int64_t pf_workspace_bytes(pf_handle h, int n, int max_h) {
   Fwd F{h, Arena{}, nullptr, true, n};
   F.ar.dry = true;
   F.ar.keep = h->debug;
-  int r = run_forward(F, nullptr, max_h);
+  int r = h->use_tma ? run_forward_tma(F, nullptr) : run_forward(F, nullptr, max_h);
   if (r != PF_OK) return r;
   return F.ar.peak + 4096;
 }
@@ -659,12 +986,12 @@ int pf_forward(pf_handle h, const pf_batch* bt, void* workspace, int64_t workspa
   {  // capacity check with a dry run (cheap: no launches)
     Fwd T{h, Arena{}, nullptr, true, bt->n};
     T.ar.dry = true; T.ar.keep = h->debug;
-    TRY(run_forward(T, nullptr, 0));
+    TRY(h->use_tma ? run_forward_tma(T, nullptr) : run_forward(T, nullptr, 0));
     if (T.ar.peak > workspace_bytes) return fail(PF_ERR_WORKSPACE, "pf_forward: workspace %lld B < required %lld B", (long long)workspace_bytes, T.ar.peak);
   }
   if (((uintptr_t)workspace & 255) != 0) return fail(PF_ERR_ARG, "pf_forward: workspace must be 256-byte aligned");
   h->taps.clear();
-  return run_forward(F, bt, 0);
+  return h->use_tma ? run_forward_tma(F, bt) : run_forward(F, bt, 0);
 }
 
 int pf_profile_enable(pf_handle h, int on) {
@@ -682,13 +1009,14 @@ int pf_set_option(pf_handle h, const char* name, int value) {
   if (!h || !name) return fail(PF_ERR_ARG, "pf_set_option: null argument");
   if (!strcmp(name, "tcgen05")) { h->use_tc = value != 0; return PF_OK; }
   if (!strcmp(name, "halo3x3")) { h->use_halo = value != 0; return PF_OK; }
+  if (!strcmp(name, "tma")) { h->use_tma = value != 0; return PF_OK; }
   return fail(PF_ERR_ARG, "pf_set_option: unknown option '%s'", name);
 }
-// out[cfg*3 + {0,1,2}] = {milliseconds, algorithmic FLOPs, launches} per GEMM engine configuration (5 configs),
+// out[cfg*3 + {0,1,2}] = {milliseconds, algorithmic FLOPs, launches} per GEMM engine configuration (7 configs),
 // accumulated since the last read; the caller must have synchronised the stream.
 int pf_profile_read(pf_handle h, double* out9) {
   if (!h || !out9) return fail(PF_ERR_ARG, "pf_profile_read: null argument");
-  for (int i = 0; i < 15; ++i) out9[i] = 0.0;
+  for (int i = 0; i < 21; ++i) out9[i] = 0.0;
   FILE* csv = nullptr;
   if (const char* path = getenv("PF_PROFILE_CSV")) {   // optional per-launch dump (profiles/)
     csv = fopen(path, "w");
@@ -746,6 +1074,38 @@ int pf_op_conv_gemm(const float* x, int B, int H, int W, int Cin, const void* wh
   p.bias = bias; p.bias_mode = bias ? 1 : 0; p.act = act;
   p.res = res; p.ldr = N; p.res_relu = res_relu;
   p.C = y; p.ldc = N; p.groups = 1;
+  if (engine == 3) {
+    // TMA engine: split the input the way a producer kernel would, then run the same helpers the forward graph uses
+    if (KH != KW) return fail(PF_ERR_ARG, "pf_op_conv_gemm: square filters only");
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, dev));
+    static pf_engine tmp;
+    tmp.sm_count = prop.multiProcessorCount;
+    tmp.profile = false; tmp.debug = false;
+    const long long nx = (long long)B * H * W * Cin;
+    const long long colb = (long long)B * p.OH * p.OW * KH * KW * Cin * 4 + (1 << 20);
+    char* scratch = nullptr;
+    CU(cudaMalloc(&scratch, nx * 4 + colb + 4096));
+    Fwd F{&tmp, Arena{}, st, false, B};
+    F.ar.base = scratch; F.ar.cap = nx * 4 + colb + 4096;
+    SplitT A = F.salloc((long long)B * H * W, Cin);
+    LAUNCHED((split_kernel<<<(unsigned)cdivl(nx, 256), 256, 0, st>>>(x, A.hi, A.lo, nx, in_relu), cudaGetLastError()));
+    GemmW w{(const __nv_bfloat16*)whi, (const __nv_bfloat16*)wlo, bias};
+    Fwd::Epi o;
+    o.C = y; o.ldc = N; o.act = act; o.res = res; o.ldr = N; o.res_relu = res_relu;
+    int r;
+    if (KH == 3 && stride == 1 && pad == 1 && Cin % 64 == 0) r = F.thalo(A, 0, 0, nullptr, 0, 0, B, H, W, Cin, w, N, 1, 0, o);
+    else if (KH == 1 && stride == 1 && pad == 0) r = F.tgemm(A, (long long)B * H * W, Cin, 0, w, N, o);
+    else r = F.tconv_gather(A, B, H, W, Cin, KH, stride, pad, w, N, o);
+    cudaError_t se = cudaStreamSynchronize(st);
+    cudaFree(scratch);
+    if (r != PF_OK) return r;
+    if (se != cudaSuccess) return fail(PF_ERR_CUDA, "TMA engine: %s", cudaGetErrorString(se));
+    return PF_OK;
+  }
   if (engine == 2) {
     if (!conv3x3_tc_eligible(p)) return fail(PF_ERR_ARG, "pf_op_conv_gemm: shape not eligible for the halo-tile 3x3 kernel");
     LAUNCHED(conv3x3_tc_launch(p, (cudaStream_t)stream));

@@ -179,18 +179,22 @@ def test_kernel_launches_are_counted():
     assert _native.lib().pf_kernel_launch_count() - before > 300
 
 
-def test_hmma_engine_end_to_end():
-    """The same forward with every GEMM on the warp-level HMMA kernel instead of the (default) tcgen05/TMEM kernel."""
+@pytest.mark.parametrize("opts", [{"tma": 0}, {"tma": 0, "halo3x3": 0}, {"tma": 0, "tcgen05": 0}])
+def test_legacy_engines_end_to_end(opts):
+    """The same forward on the earlier engines (fp32 activations split on the fly): register-staged tcgen05 kernels with
+    / without the halo-tile 3x3 variant, and the warp-level HMMA kernel."""
     version = "Paramnet-360Cities-edina-centered"
     m, sd = model(version)
     imgs = golden_images()
     base = m.inference_batch(imgs)
-    m.set_option("tcgen05", 0)
+    for k, v in opts.items():
+        m.set_option(k, v)
     try:
         out = m.inference_batch(imgs)
     finally:
-        m.set_option("tcgen05", 1)
-    print("hmma", _check(out, om.inference_batch(sd, version, imgs), version))
+        for k in opts:
+            m.set_option(k, 1)
+    print(opts, _check(out, om.inference_batch(sd, version, imgs), version))
     compare_with_golden(version, out, tol=TOL)
     for a, b in zip(out, base):
         assert U.rel_err(a["pred_latitude"], b["pred_latitude"]) < 1e-4

@@ -200,3 +200,42 @@ def test_conv3x3_halo_tcgen05(case):
     assert U.rel_err(y.permute(0, 3, 1, 2), ref) < 5e-5
     # same products, different fp32 summation order (channel chunks outermost instead of filter taps)
     assert U.rel_err(y, U.conv_gemm(xh, w, b, 1, 1, ir, act, r, rr, engine=0)) < 2e-5
+
+
+# ---- TMA -> tcgen05 engine (engine 3): inputs are split into bf16 hi/lo planes first, exactly as the forward graph does
+@pytest.mark.parametrize("case", GEMM_CASES + TC_CASES[:3])
+def test_conv_gemm_tma_engine(case):
+    B, H, W, Cin, N, K, s, p, ir, act, res, rr = case
+    if N % 32:
+        pytest.skip("TMA engine needs N % 32 == 0")
+    g = torch.Generator().manual_seed(hash(case) & 0xFFFF)
+    x = _rn(g, B, Cin, H, W).cuda()
+    w = _rn(g, N, Cin, K, K) / (Cin * K * K) ** 0.5
+    b = _rn(g, N)
+    ref = F.conv2d((F.relu(x) if ir else x).double(), w.double().cuda(), b.double().cuda(), stride=s, padding=p)
+    ref = F.relu(ref) if act == 1 else (F.gelu(ref) if act == 2 else ref)
+    r = None
+    if res:
+        r = _rn(g, *ref.shape).cuda()
+        ref = ref + (F.relu(r) if rr else r).double()
+        r = r.permute(0, 2, 3, 1).contiguous()
+    y = U.conv_gemm(x.permute(0, 2, 3, 1).contiguous(), w, b, s, p, ir, act, r, rr, engine=3)
+    assert U.rel_err(y.permute(0, 3, 1, 2), ref) < 5e-5
+
+
+@pytest.mark.parametrize("case", HALO_CASES)
+def test_conv3x3_tma_halo(case):
+    B, H, W, Cin, N, ir, act, res, rr = case
+    g = torch.Generator().manual_seed(hash(case) & 0xFFFF)
+    x = _rn(g, B, Cin, H, W).cuda()
+    w = _rn(g, N, Cin, 3, 3) / (Cin * 9) ** 0.5
+    b = _rn(g, N)
+    ref = F.conv2d((F.relu(x) if ir else x).double(), w.double().cuda(), b.double().cuda(), padding=1)
+    ref = F.relu(ref) if act == 1 else ref
+    r = None
+    if res:
+        r = _rn(g, *ref.shape).cuda()
+        ref = ref + (F.relu(r) if rr else r).double()
+        r = r.permute(0, 2, 3, 1).contiguous()
+    y = U.conv_gemm(x.permute(0, 2, 3, 1).contiguous(), w, b, 1, 1, ir, act, r, rr, engine=3)
+    assert U.rel_err(y.permute(0, 3, 1, 2), ref) < 5e-5

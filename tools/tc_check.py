@@ -30,6 +30,29 @@ for (B, H, W, Cin, N, K, s, p, ir, act, res, rr) in cases:
     except Exception as ex:
         print("EXC", type(ex).__name__, str(ex)[:300], flush=True)
         break
+print("--- TMA engine (engine 3)", flush=True)
+for (B, H, W, Cin, N, K, s, p, ir, act, res, rr) in [(1, 1, 128, 32, 256, 1, 1, 0, 0, 0, 0, 0), (1, 1, 300, 320, 256, 1, 1, 0, 0, 0, 0, 0), (1, 1, 700, 320, 640, 1, 1, 0, 0, 0, 0, 0),
+        (1, 1, 130, 384, 96, 1, 1, 0, 0, 0, 1, 0), (1, 1, 5000, 64, 320, 1, 1, 0, 0, 2, 0, 0), (2, 80, 80, 64, 64, 8, 8, 0, 0, 0, 0, 0), (2, 40, 40, 64, 128, 3, 2, 1, 0, 0, 0, 0),
+        (1, 16, 8, 64, 32, 3, 1, 1, 0, 0, 0, 0), (2, 23, 17, 256, 256, 3, 1, 1, 1, 1, 1, 1), (1, 10, 10, 512, 512, 3, 1, 1, 0, 0, 0, 0), (1, 40, 40, 320, 64, 3, 1, 1, 0, 1, 0, 0), (4, 80, 80, 256, 256, 3, 1, 1, 1, 1, 0, 0)]:
+    x = rn(B, Cin, H, W).cuda(); w = rn(N, Cin, K, K) / (Cin * K * K) ** 0.5; b = rn(N)
+    ref = F.conv2d((F.relu(x) if ir else x).double(), w.double().cuda(), b.double().cuda(), stride=s, padding=p)
+    if act == 1: ref = F.relu(ref)
+    if act == 2: ref = F.gelu(ref)
+    r = None
+    if res:
+        r = rn(*ref.shape).cuda(); ref = ref + (F.relu(r) if rr else r).double(); r = r.permute(0, 2, 3, 1).contiguous()
+    xh = x.permute(0, 2, 3, 1).contiguous()
+    try:
+        y = U.conv_gemm(xh, w, b, s, p, ir, act, r, rr, engine=3)
+        e = U.rel_err(y.permute(0, 3, 1, 2), ref)
+        print(f"tma B{B} {H}x{W} Cin{Cin} N{N} k{K} s{s}: rel vs fp64 {e:.3g}", flush=True)
+        if e > 1e-3:
+            d = (y.permute(0, 3, 1, 2).double() - ref).abs()
+            print("   bad: argmax", [int(v) for v in torch.unravel_index(d.argmax(), d.shape)], "per-chan max", [round(float(v), 3) for v in d.amax(dim=(0, 2, 3))[:12]],
+                  "per-row max", [round(float(v), 3) for v in d.amax(dim=(0, 1, 3))[:20]], flush=True)
+    except Exception as ex:
+        print("EXC", type(ex).__name__, str(ex)[:300], flush=True)
+        break
 print("--- halo-tile 3x3 kernel", flush=True)
 for (B, H, W, Cin, N, ir, act, res, rr) in [(1, 16, 8, 64, 32, 0, 0, 0, 0), (2, 16, 8, 64, 32, 0, 1, 0, 0), (1, 80, 80, 256, 256, 1, 1, 0, 0), (2, 23, 17, 256, 256, 0, 0, 1, 1),
                                              (1, 10, 10, 512, 512, 0, 0, 0, 0), (1, 40, 40, 320, 64, 0, 1, 0, 0), (3, 33, 9, 128, 128, 0, 0, 0, 0)]:
