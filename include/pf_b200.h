@@ -101,7 +101,8 @@ int pf_profile_read(pf_handle h, double* out21);
 /* Engine options.  "tma" (default 1): the forward graph runs on the persistent TMA -> tcgen05 -> TMEM engine with pre-split
  * bf16 hi/lo activations (gemm_tma.cuh).  With "tma" = 0 the earlier engines are used (fp32 activations split on the fly):
  * "tcgen05" (default 1) selects the register-staged tcgen05 kernels over the warp-level HMMA kernel, "halo3x3" (default 1)
- * the halo-tile variant for 3x3/stride-1 convolutions.  All engines evaluate the same bf16x3 products. */
+ * the halo-tile variant for 3x3/stride-1 convolutions.  All engines evaluate the same bf16x3 products.
+ * "attn_mma" (default 1, TMA graph only): attention core on the tensor cores (attention_mma.cuh) instead of CUDA cores. */
 int pf_set_option(pf_handle h, const char* name, int value);
 
 /* Debug taps (tests only): when enabled, intermediates of the next pf_forward are kept (never recycled) and can be
@@ -121,7 +122,8 @@ int pf_op_conv_gemm(const float* x, int B, int H, int W, int Cin, const void* wh
                     int N, int KH, int KW, int stride, int pad, int in_relu, int act, const float* res, int res_relu,
                     float* y, int engine /* 0 = HMMA, 1 = tcgen05 generic, 2 = tcgen05 halo-tile 3x3, 3 = TMA engine */, void* stream);
 int pf_op_layernorm(const float* x, float* y, int64_t rows, int C, const float* w, const float* b, float eps, void* stream);
-int pf_op_attention(const float* q, const float* kv, float* out, int B, int N, int C, int heads, void* stream);
+int pf_op_attention(const float* q, const float* kv, float* out, int B, int N, int C, int heads, void* stream);      /* CUDA-core fp32 */
+int pf_op_attention_mma(const float* q, const float* kv, float* out, int B, int N, int C, int heads, void* stream);  /* tensor cores, bf16x3 */
 int pf_op_dwconv3x3_gelu(const float* x, float* y, int B, int H, int W, int C, const float* w9c, const float* bias, void* stream);
 int pf_op_dwconv7x7(const float* x, float* y, int B, int H, int W, int C, const float* w49c, const float* bias, void* stream);
 int pf_op_upsample2x(const float* x, float* y, int B, int H, int W, int C, void* stream);

@@ -98,6 +98,7 @@ def lib():
         "pf_set_option": (i32, [vp, ctypes.c_char_p, i32]),
         "pf_op_layernorm": (i32, [vp, vp, i64, i32, vp, vp, f32, vp]),
         "pf_op_attention": (i32, [vp, vp, vp, i32, i32, i32, i32, vp]),
+        "pf_op_attention_mma": (i32, [vp, vp, vp, i32, i32, i32, i32, vp]),
         "pf_op_dwconv3x3_gelu": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp]),
         "pf_op_dwconv7x7": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp]),
         "pf_op_upsample2x": (i32, [vp, vp, i32, i32, i32, i32, vp]),
@@ -114,7 +115,7 @@ def lib():
 
 EXPORTS = ["pf_abi_version", "pf_last_error", "pf_kernel_launch_count", "pf_create", "pf_destroy", "pf_set_weight",
            "pf_finalize", "pf_workspace_bytes", "pf_forward", "pf_profile_enable", "pf_profile_read", "pf_set_option", "pf_debug_enable", "pf_debug_count", "pf_debug_name",
-           "pf_debug_numel", "pf_debug_copy", "pf_op_conv_gemm", "pf_op_layernorm", "pf_op_attention",
+           "pf_debug_numel", "pf_debug_copy", "pf_op_conv_gemm", "pf_op_layernorm", "pf_op_attention", "pf_op_attention_mma",
            "pf_op_dwconv3x3_gelu", "pf_op_dwconv7x7", "pf_op_upsample2x", "pf_op_preprocess"]
 
 

@@ -36,6 +36,7 @@ struct TmaGemmParams {
   int a_c0, a_gc;           // channel coordinate of the first input channel in A's tensor map, step per group
   int c_split, a2_c0;       // MODE_HALO dual source: input channels >= c_split come from the A2 maps at a2_c0 + (ci - c_split); 0 = off
   int groups;
+  int b_row0;               // first row of this launch's weights in the B tensor map (resident-weight launches fold the group in)
   // epilogue:  v = acc + bias;  v = act(v);  v *= gamma;  v += relu?(res);  v += res2
   const float* bias; int bias_mode, bias_gstride;
   int act; const float* gamma;
@@ -45,9 +46,12 @@ struct TmaGemmParams {
   __nv_bfloat16* Shi; __nv_bfloat16* Slo; int lds, s_coff, s_gcoff, split_relu; // split output (may be null)
 };
 
-template <int BN, int MODE> struct TmaCfg {
-  static constexpr int kBPlane = BN * 64;                       // bf16 plane of a 32-wide K step of B
-  static constexpr int kAPlane = 128 * 64;                      // MODE_GEMM: plane of a 128 x 32 A tile
+// KB = K elements per pipeline step: 32 (64 B rows, SWIZZLE_64B) for wide tiles, 64 (128 B rows, SWIZZLE_128B) for BN <= 128
+// where a 32-wide step would be shorter than the barrier round trip that feeds it.
+template <int BN, int MODE, int KB> struct TmaCfg {
+  static_assert(KB == 32 || KB == 64, "KB");
+  static constexpr int kBPlane = BN * KB * 2;                   // bf16 plane of one K step of B
+  static constexpr int kAPlane = 128 * KB * 2;                  // MODE_GEMM: plane of a 128 x KB A tile
   static constexpr int kStage = (MODE == MODE_GEMM ? 2 * kAPlane : 0) + 2 * kBPlane;
   static constexpr int kABuf = 2 * kHtPlaneBytes;               // MODE_HALO: hi + lo halo planes (1024 B multiples)
   static constexpr int kBudget = 225 * 1024 - (MODE == MODE_HALO ? 2 * kABuf : 0);
@@ -59,6 +63,14 @@ template <int BN, int MODE> struct TmaCfg {
   static_assert(kStages >= 3, "ring too shallow");
   static_assert(2 * BN <= 512, "two accumulators must fit TMEM");
 };
+
+// K-major operand descriptor for a tile whose rows are KB bf16 wide (KB = 32: SWIZZLE_64B, 8-row groups 512 B apart;
+// KB = 64: SWIZZLE_128B, 1024 B apart)
+template <int KB>
+__device__ __forceinline__ uint64_t tma_tile_desc(uint32_t smem_addr) {
+  constexpr uint64_t sbo = KB == 32 ? 512 : 1024, layout = KB == 32 ? 4 : 2;
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((sbo >> 4) << 32) | ((uint64_t)1 << 46) | (layout << 61);
+}
 
 // ------------------------------------------------------------------------------------------------ TMA PTX
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -80,10 +92,11 @@ struct TmaMaps {   // passed by value as a __grid_constant__ kernel parameter
   CUtensorMap a_hi, a_lo, a2_hi, a2_lo, b_hi, b_lo;
 };
 
-template <int BN, int MODE>
+template <int BN, int MODE, int KB>
 __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_constant__ TmaMaps maps, const TmaGemmParams p, int tiles_x, int tiles_y) {
-  using Cfg = TmaCfg<BN, MODE>;
+  using Cfg = TmaCfg<BN, MODE, KB>;
   constexpr int NS = Cfg::kStages;
+  constexpr int SPC = 9 * (64 / KB);          // MODE_HALO: pipeline steps per 64-channel chunk (9 taps x 64 / KB)
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t raw = smem_u32(smem_dyn);
   const uint32_t sbase = (raw + 1023u) & ~1023u;
@@ -104,7 +117,10 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
   const int m_tiles = MODE == MODE_GEMM ? cdiv(p.M, 128) : p.B * tiles_x * tiles_y;
   const int total_tiles = m_tiles * n_tiles * p.groups;
   const int nchunks = MODE == MODE_HALO ? p.Cin / 64 : 0;
-  const int nk = MODE == MODE_GEMM ? p.K / 32 : nchunks * 18;
+  const int nk = MODE == MODE_GEMM ? p.K / KB : nchunks * SPC;
+  // MODE_HALO with a single chunk whose 9 taps fit the ring (conv_fuse_conv1): the weights are loaded once per CTA and stay
+  // resident for all of its tiles instead of being re-streamed from L2 for every tile.
+  const bool b_resident = MODE == MODE_HALO && nchunks == 1 && SPC <= NS;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.a_hi); tma_prefetch_desc(&maps.a_lo); tma_prefetch_desc(&maps.b_hi); tma_prefetch_desc(&maps.b_lo);
@@ -133,7 +149,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int mt, g, n0;
         decode(tile, mt, g, n0);
-        const int brow = g * p.N + n0;
+        const int brow = p.b_row0 + g * p.N + n0;
+        if (b_resident && it > 0) break;     // resident weights: loaded with the first tile only (one group / N tile per launch)
         for (int kc = 0; kc < nk; ++kc, ++it) {
           const int s = it % NS;
           mbar_wait(empty_b(s), ((it / NS) & 1) ^ 1);
@@ -141,12 +158,12 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
           const uint32_t st = ring + s * Cfg::kStage;
           int kcol;
           if (MODE == MODE_GEMM) {
-            kcol = kc * 32;
+            kcol = kc * KB;
             tma_load_2d(st, &maps.a_hi, full_b(s), p.a_c0 + g * p.a_gc + kcol, mt * 128);
             tma_load_2d(st + Cfg::kAPlane, &maps.a_lo, full_b(s), p.a_c0 + g * p.a_gc + kcol, mt * 128);
           } else {
-            const int c = kc / 18, u = kc - c * 18;
-            kcol = (u >> 1) * p.Cin + c * 64 + (u & 1) * 32;
+            const int c = kc / SPC, u = kc - c * SPC;
+            kcol = KB == 32 ? (u >> 1) * p.Cin + c * 64 + (u & 1) * 32 : u * p.Cin + c * 64;
           }
           const uint32_t bdst = st + (MODE == MODE_GEMM ? 2 * Cfg::kAPlane : 0);
           tma_load_2d(bdst, &maps.b_hi, full_b(s), kcol, brow);
@@ -192,33 +209,34 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
         int a_kbase = 0;
         bool chunk_end = false;
         if (MODE == MODE_HALO) {
-          const int c = kc / 18, u = kc - c * 18;
-          const int tap = u >> 1, ky = tap / 3, kx = tap - ky * 3;
+          const int c = kc / SPC, u = kc - c * SPC;
+          const int tap = KB == 32 ? (u >> 1) : u, ky = tap / 3, kx = tap - ky * 3;
           const int buf = ita & 1;
           if (u == 0) mbar_wait(full_a(buf), (ita >> 1) & 1);
           a_hi = a_base + buf * Cfg::kABuf + (ky * kHtHaloW + kx) * 128;
           a_lo = a_hi + kHtPlaneBytes;
-          a_kbase = (u & 1) * 64;                         // second half of the 128 B pixel row
-          chunk_end = u == 17;
+          a_kbase = KB == 32 ? (u & 1) * 64 : 0;          // KB = 32: second half of the 128 B pixel row
+          chunk_end = u == SPC - 1;
         } else {
           a_hi = ring + s * Cfg::kStage;
           a_lo = a_hi + Cfg::kAPlane;
         }
-        mbar_wait(full_b(s), (it / NS) & 1);
+        const int sb = b_resident ? kc : s;                                   // resident weights: step kc lives in slot kc
+        if (!b_resident || tl == 0) mbar_wait(full_b(sb), b_resident ? 0 : ((it / NS) & 1));
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t b_hi = ring + s * Cfg::kStage + (MODE == MODE_GEMM ? 2 * Cfg::kAPlane : 0), b_lo = b_hi + Cfg::kBPlane;
+          const uint32_t b_hi = ring + sb * Cfg::kStage + (MODE == MODE_GEMM ? 2 * Cfg::kAPlane : 0), b_lo = b_hi + Cfg::kBPlane;
 #pragma unroll
-          for (int kk = 0; kk < 2; ++kk) {
+          for (int kk = 0; kk < KB / 16; ++kk) {
             uint64_t dah, dal;
             if (MODE == MODE_HALO) { dah = ht_a_desc(a_hi + a_kbase + kk * 32); dal = ht_a_desc(a_lo + a_kbase + kk * 32); }
-            else { dah = tc_smem_desc(a_hi + kk * 32); dal = tc_smem_desc(a_lo + kk * 32); }
-            const uint64_t dbh = tc_smem_desc(b_hi + kk * 32), dbl = tc_smem_desc(b_lo + kk * 32);
+            else { dah = tma_tile_desc<KB>(a_hi + kk * 32); dal = tma_tile_desc<KB>(a_lo + kk * 32); }
+            const uint64_t dbh = tma_tile_desc<KB>(b_hi + kk * 32), dbl = tma_tile_desc<KB>(b_lo + kk * 32);
             umma_bf16(acc, dal, dbh, Cfg::kIdesc, (kc | kk) ? 1u : 0u);
             umma_bf16(acc, dah, dbl, Cfg::kIdesc, 1u);
             umma_bf16(acc, dah, dbh, Cfg::kIdesc, 1u);
           }
-          umma_commit(empty_b(s));
+          if (!b_resident) umma_commit(empty_b(s));
           if (MODE == MODE_HALO && chunk_end) umma_commit(empty_a(ita & 1));
           if (kc == nk - 1) umma_commit(tmem_full(as));
         }

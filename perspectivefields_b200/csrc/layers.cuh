@@ -78,49 +78,53 @@ inline cudaError_t stem_conv_launch(const float* in, int ldin, int B, int H, int
 // LayerNorm over the channel dimension of [rows, C] (nn.LayerNorm / F.layer_norm, biased variance, eps inside
 // the sqrt) -- mix_transformers.py:199-200,247,120,457 and convnext.py:172-182 (both data formats reduce to this
 // in NHWC).  One warp per row; two-pass (mean, then centred variance) in registers.
-template <int MAXPER>
+template <int MAXQ>   // float4 quads per lane: lane owns channels [4*(lane + 32*i), +4)
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ in, float* __restrict__ out, long long rows, int C,
                                                         const float* __restrict__ gw, const float* __restrict__ gb, float eps,
                                                         __nv_bfloat16* __restrict__ shi, __nv_bfloat16* __restrict__ slo) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
-  const float* x = in + row * C;
-  float v[MAXPER];
+  const int Q = C >> 2;
+  const float4* x = reinterpret_cast<const float4*>(in + row * C);
+  float4 v[MAXQ];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXPER; ++i) {
-    const int c = lane + 32 * i;
-    v[i] = c < C ? x[c] : 0.f;
-    s += v[i];
+  for (int i = 0; i < MAXQ; ++i) {
+    const int qd = lane + 32 * i;
+    v[i] = qd < Q ? x[qd] : make_float4(0.f, 0.f, 0.f, 0.f);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   }
   const float mean = warp_sum(s) / (float)C;
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXPER; ++i) {
-    const int c = lane + 32 * i;
-    const float d = c < C ? v[i] - mean : 0.f;
-    q = fmaf(d, d, q);
+  for (int i = 0; i < MAXQ; ++i) {
+    if (lane + 32 * i < Q) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q = fmaf(a, a, q); q = fmaf(b, b, q); q = fmaf(c, c, q); q = fmaf(d, d, q);
+    }
   }
   const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
 #pragma unroll
-  for (int i = 0; i < MAXPER; ++i) {
-    const int c = lane + 32 * i;
-    if (c < C) {
-      const float y = (v[i] - mean) * rstd * __ldg(gw + c) + __ldg(gb + c);
-      if (out) out[row * C + c] = y;
-      if (shi) store_split1(shi, slo, row * C + c, y);
+  for (int i = 0; i < MAXQ; ++i) {
+    const int qd = lane + 32 * i;
+    if (qd < Q) {
+      const float4 w = __ldg(reinterpret_cast<const float4*>(gw) + qd), b = __ldg(reinterpret_cast<const float4*>(gb) + qd);
+      const float4 y = make_float4((v[i].x - mean) * rstd * w.x + b.x, (v[i].y - mean) * rstd * w.y + b.y,
+                                   (v[i].z - mean) * rstd * w.z + b.z, (v[i].w - mean) * rstd * w.w + b.w);
+      if (out) reinterpret_cast<float4*>(out + row * C)[qd] = y;
+      if (shi) store_split4(shi, slo, row * C + qd * 4, y);
     }
   }
 }
 
 inline cudaError_t layernorm_launch(const float* in, float* out, long long rows, int C, const float* w, const float* b, float eps,
                                     cudaStream_t st, SplitT sp = SplitT()) {
+  if (C % 4 || C > 768) return cudaErrorInvalidValue;
   const unsigned grid = (unsigned)cdivl(rows, 8);
-  if (C <= 128) layernorm_kernel<4><<<grid, 256, 0, st>>>(in, out, rows, C, w, b, eps, sp.hi, sp.lo);
-  else if (C <= 384) layernorm_kernel<12><<<grid, 256, 0, st>>>(in, out, rows, C, w, b, eps, sp.hi, sp.lo);
-  else if (C <= 768) layernorm_kernel<24><<<grid, 256, 0, st>>>(in, out, rows, C, w, b, eps, sp.hi, sp.lo);
-  else return cudaErrorInvalidValue;
+  if (C <= 128) layernorm_kernel<1><<<grid, 256, 0, st>>>(in, out, rows, C, w, b, eps, sp.hi, sp.lo);
+  else if (C <= 384) layernorm_kernel<3><<<grid, 256, 0, st>>>(in, out, rows, C, w, b, eps, sp.hi, sp.lo);
+  else layernorm_kernel<6><<<grid, 256, 0, st>>>(in, out, rows, C, w, b, eps, sp.hi, sp.lo);
   return cudaGetLastError();
 }
 
@@ -217,57 +221,86 @@ inline cudaError_t attention_launch(const float* q, const float* kv, float* out,
 __global__ void __launch_bounds__(256) dwconv3x3_gelu_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C,
                                                              const float* __restrict__ w, const float* __restrict__ bias,
                                                              __nv_bfloat16* __restrict__ shi = nullptr, __nv_bfloat16* __restrict__ slo = nullptr) {
-  const int C4 = C >> 2;
-  const long long total = (long long)B * H * W * C4;
+  // thread = 4 channels x 4 consecutive pixels of one row: 18 activation + 9 weight loads for 4 outputs
+  const int C4 = C >> 2, XG = (W + 3) >> 2;
+  const long long total = (long long)B * H * XG * C4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c4 = (int)(i % C4);
-    long long pix = i / C4;
-    const int x = (int)(pix % W); pix /= W;
-    const int y = (int)(pix % H); const int b = (int)(pix / H);
-    float4 acc = __ldg(reinterpret_cast<const float4*>(bias) + c4);
+    long long r = i / C4;
+    const int xg = (int)(r % XG); r /= XG;
+    const int y = (int)(r % H); const int b = (int)(r / H);
+    const int x0 = xg * 4;
+    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias) + c4);
+    float4 acc[4] = {bv, bv, bv, bv};
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       const int iy = y + ky - 1;
       if ((unsigned)iy >= (unsigned)H) continue;
+      float4 a[6];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const int ix = x0 - 1 + j;
+        a[j] = (unsigned)ix < (unsigned)W ? __ldg(reinterpret_cast<const float4*>(in + ((long long)(b * H + iy) * W + ix) * C) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
-        const int ix = x + kx - 1;
-        if ((unsigned)ix >= (unsigned)W) continue;
-        const float4 v = __ldg(reinterpret_cast<const float4*>(in + ((long long)(b * H + iy) * W + ix) * C) + c4);
         const float4 k = __ldg(reinterpret_cast<const float4*>(w + (ky * 3 + kx) * C) + c4);
-        acc.x = fmaf(v.x, k.x, acc.x); acc.y = fmaf(v.y, k.y, acc.y); acc.z = fmaf(v.z, k.z, acc.z); acc.w = fmaf(v.w, k.w, acc.w);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          acc[p].x = fmaf(a[p + kx].x, k.x, acc[p].x); acc[p].y = fmaf(a[p + kx].y, k.y, acc[p].y);
+          acc[p].z = fmaf(a[p + kx].z, k.z, acc[p].z); acc[p].w = fmaf(a[p + kx].w, k.w, acc[p].w);
+        }
       }
     }
-    const float4 r = make_float4(gelu_erf(acc.x), gelu_erf(acc.y), gelu_erf(acc.z), gelu_erf(acc.w));
-    if (out) reinterpret_cast<float4*>(out)[i] = r;
-    if (shi) store_split4(shi, slo, i * 4, r);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      if (x0 + p >= W) break;
+      const float4 o = make_float4(gelu_erf(acc[p].x), gelu_erf(acc[p].y), gelu_erf(acc[p].z), gelu_erf(acc[p].w));
+      const long long oi = ((long long)(b * H + y) * W + x0 + p) * C + c4 * 4;
+      if (out) *reinterpret_cast<float4*>(out + oi) = o;
+      if (shi) store_split4(shi, slo, oi, o);
+    }
   }
 }
 
 // Depthwise 7x7 conv (pad 3) + bias on NHWC -- ConvNeXt block head, convnext.py:28-30,48.  w: [49][C].
+// thread = 4 channels x 4 consecutive pixels of one row: per filter row 10 activation + 7 weight loads for 28 tap-pixels.
 __global__ void __launch_bounds__(256) dwconv7x7_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C,
                                                         const float* __restrict__ w, const float* __restrict__ bias) {
-  const int C4 = C >> 2;
-  const long long total = (long long)B * H * W * C4;
+  const int C4 = C >> 2, XG = (W + 3) >> 2;
+  const long long total = (long long)B * H * XG * C4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c4 = (int)(i % C4);
-    long long pix = i / C4;
-    const int x = (int)(pix % W); pix /= W;
-    const int y = (int)(pix % H); const int b = (int)(pix / H);
-    float4 acc = __ldg(reinterpret_cast<const float4*>(bias) + c4);
+    long long r = i / C4;
+    const int xg = (int)(r % XG); r /= XG;
+    const int y = (int)(r % H); const int b = (int)(r / H);
+    const int x0 = xg * 4;
+    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias) + c4);
+    float4 acc[4] = {bv, bv, bv, bv};
     for (int ky = 0; ky < 7; ++ky) {
       const int iy = y + ky - 3;
       if ((unsigned)iy >= (unsigned)H) continue;
+      float4 a[10];
+#pragma unroll
+      for (int j = 0; j < 10; ++j) {
+        const int ix = x0 - 3 + j;
+        a[j] = (unsigned)ix < (unsigned)W ? __ldg(reinterpret_cast<const float4*>(in + ((long long)(b * H + iy) * W + ix) * C) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
 #pragma unroll
       for (int kx = 0; kx < 7; ++kx) {
-        const int ix = x + kx - 3;
-        if ((unsigned)ix >= (unsigned)W) continue;
-        const float4 v = __ldg(reinterpret_cast<const float4*>(in + ((long long)(b * H + iy) * W + ix) * C) + c4);
         const float4 k = __ldg(reinterpret_cast<const float4*>(w + (ky * 7 + kx) * C) + c4);
-        acc.x = fmaf(v.x, k.x, acc.x); acc.y = fmaf(v.y, k.y, acc.y); acc.z = fmaf(v.z, k.z, acc.z); acc.w = fmaf(v.w, k.w, acc.w);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          acc[p].x = fmaf(a[p + kx].x, k.x, acc[p].x); acc[p].y = fmaf(a[p + kx].y, k.y, acc[p].y);
+          acc[p].z = fmaf(a[p + kx].z, k.z, acc[p].z); acc[p].w = fmaf(a[p + kx].w, k.w, acc[p].w);
+        }
       }
     }
-    reinterpret_cast<float4*>(out)[i] = acc;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      if (x0 + p >= W) break;
+      *reinterpret_cast<float4*>(out + ((long long)(b * H + y) * W + x0 + p) * C + c4 * 4) = acc[p];
+    }
   }
 }
 
@@ -283,30 +316,43 @@ inline unsigned ew_grid(long long total) {
 // `in` channel pitch/offset (ldi, icoff) select one head's half of a 512-channel tensor.
 __global__ void __launch_bounds__(256) upsample2x_kernel(const float* __restrict__ in, int ldi, int icoff, float* __restrict__ out, int ldo, int ocoff,
                                                          int B, int H, int W, int C, __nv_bfloat16* __restrict__ shi = nullptr, __nv_bfloat16* __restrict__ slo = nullptr) {
-  const int C4 = C >> 2, OH = 2 * H, OW = 2 * W;
-  const long long total = (long long)B * OH * OW * C4;
+  // thread = 8 channels of one output pixel (16 B stores to each bf16 plane)
+  const int C8 = C >> 3, OH = 2 * H, OW = 2 * W;
+  const long long total = (long long)B * OH * OW * C8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c4 = (int)(i % C4);
-    long long pix = i / C4;
+    const int c8 = (int)(i % C8);
+    long long pix = i / C8;
     const int x = (int)(pix % OW); pix /= OW;
     const int y = (int)(pix % OH); const int b = (int)(pix / OH);
     const float sy = fmaxf(0.5f * (y + 0.5f) - 0.5f, 0.f), sx = fmaxf(0.5f * (x + 0.5f) - 0.5f, 0.f);
     const int y0 = (int)sy, x0 = (int)sx;
     const int y1 = y0 + (y0 < H - 1), x1 = x0 + (x0 < W - 1);
     const float ly = sy - y0, lx = sx - x0, hy = 1.f - ly, hx = 1.f - lx;
-    const float* base = in + (long long)b * H * W * ldi + icoff + c4 * 4;
-    const float4 v00 = __ldg(reinterpret_cast<const float4*>(base + (long long)(y0 * W + x0) * ldi));
-    const float4 v01 = __ldg(reinterpret_cast<const float4*>(base + (long long)(y0 * W + x1) * ldi));
-    const float4 v10 = __ldg(reinterpret_cast<const float4*>(base + (long long)(y1 * W + x0) * ldi));
-    const float4 v11 = __ldg(reinterpret_cast<const float4*>(base + (long long)(y1 * W + x1) * ldi));
-    float4 r;
-    r.x = hy * (hx * v00.x + lx * v01.x) + ly * (hx * v10.x + lx * v11.x);
-    r.y = hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y);
-    r.z = hy * (hx * v00.z + lx * v01.z) + ly * (hx * v10.z + lx * v11.z);
-    r.w = hy * (hx * v00.w + lx * v01.w) + ly * (hx * v10.w + lx * v11.w);
-    const long long oi = ((long long)(b * OH + y) * OW + x) * ldo + ocoff + c4 * 4;
-    if (out) *reinterpret_cast<float4*>(out + oi) = r;
-    if (shi) store_split4(shi, slo, oi, r);
+    const float* base = in + (long long)b * H * W * ldi + icoff + c8 * 8;
+    const long long oi = ((long long)(b * OH + y) * OW + x) * ldo + ocoff + c8 * 8;
+    float4 r[2];
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const float4 v00 = __ldg(reinterpret_cast<const float4*>(base + (long long)(y0 * W + x0) * ldi + hf * 4));
+      const float4 v01 = __ldg(reinterpret_cast<const float4*>(base + (long long)(y0 * W + x1) * ldi + hf * 4));
+      const float4 v10 = __ldg(reinterpret_cast<const float4*>(base + (long long)(y1 * W + x0) * ldi + hf * 4));
+      const float4 v11 = __ldg(reinterpret_cast<const float4*>(base + (long long)(y1 * W + x1) * ldi + hf * 4));
+      r[hf].x = hy * (hx * v00.x + lx * v01.x) + ly * (hx * v10.x + lx * v11.x);
+      r[hf].y = hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y);
+      r[hf].z = hy * (hx * v00.z + lx * v01.z) + ly * (hx * v10.z + lx * v11.z);
+      r[hf].w = hy * (hx * v00.w + lx * v01.w) + ly * (hx * v10.w + lx * v11.w);
+    }
+    if (out) {
+      *reinterpret_cast<float4*>(out + oi) = r[0];
+      *reinterpret_cast<float4*>(out + oi + 4) = r[1];
+    }
+    if (shi) {
+      uint4 h, l;
+      split_bf16x2(r[0].x, r[0].y, h.x, l.x); split_bf16x2(r[0].z, r[0].w, h.y, l.y);
+      split_bf16x2(r[1].x, r[1].y, h.z, l.z); split_bf16x2(r[1].z, r[1].w, h.w, l.w);
+      *reinterpret_cast<uint4*>(shi + oi) = h;
+      *reinterpret_cast<uint4*>(slo + oi) = l;
+    }
   }
 }
 

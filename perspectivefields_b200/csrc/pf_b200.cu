@@ -20,6 +20,7 @@
 #include "conv_gemm_tc.cuh"
 #include "conv3x3_tc.cuh"
 #include "tma_host.cuh"
+#include "attention_mma.cuh"
 #include "layers.cuh"
 #include "prepost.cuh"
 
@@ -110,6 +111,7 @@ struct pf_engine {
   struct DevTable { int ksize; int* bounds; int* coeffs; };
   std::map<int, DevTable> tables;
   // per-launch profiling of the GEMM engine (bench.py roofline leg): CUDA events on the launch stream
+  bool use_attn_mma = true;   // tensor-core attention core (option "attn_mma"; 0 = CUDA-core fp32 kernel)
   bool use_tma = true;   // whole forward on the TMA -> tcgen05 engine with pre-split activations (option "tma"; 0 = legacy engines)
   int sm_count = 148;
   bool use_halo = true;  // 3x3/s1/p1 convolutions on the halo-tile tcgen05 kernel (option "halo3x3")
@@ -322,7 +324,7 @@ struct Fwd {
     return PF_OK;
   }
   int launch_tma(int mode, const TmaMaps& maps, const TmaGemmParams& p) {
-    const int bn = tma_pick_bn(p.N, mode);
+    const int bn = tma_pick_bn(p.N, mode), kb = tma_pick_kb(bn, p.K);
     if (e->profile) {
       pf_engine::ProfRec r{};
       for (cudaEvent_t* ev : {&r.a, &r.b}) {
@@ -334,12 +336,12 @@ struct Fwd {
       r.cfg = mode == MODE_GEMM ? 5 : 6;
       r.M = (int)Mrows; r.N = p.N; r.K = p.K; r.KH = mode == MODE_GEMM ? 1 : 3; r.stride = 1; r.groups = p.groups; r.Cin = p.Cin;
       CU(cudaEventRecord(r.a, st));
-      LAUNCHED(gemm_tma_launch(mode, maps, p, bn, e->sm_count, st));
+      LAUNCHED(gemm_tma_launch(mode, maps, p, bn, kb, e->sm_count, st));
       CU(cudaEventRecord(r.b, st));
       e->prof.push_back(r);
       return PF_OK;
     }
-    LAUNCHED(gemm_tma_launch(mode, maps, p, bn, e->sm_count, st));
+    LAUNCHED(gemm_tma_launch(mode, maps, p, bn, kb, e->sm_count, st));
     return PF_OK;
   }
   struct Epi {   // epilogue options of one TMA GEMM / conv
@@ -366,12 +368,12 @@ struct Fwd {
     p.M = (int)M; p.Cin = K; p.N = N; p.K = K; p.a_c0 = a_c0; p.groups = 1;
     fill_epi(p, w, o, 0);
     TmaMaps maps{};
-    const int bn = tma_pick_bn(N, MODE_GEMM);
+    const int bn = tma_pick_bn(N, MODE_GEMM), kb = tma_pick_kb(bn, K);
     const char* msg = nullptr;
-    if (!msg) msg = tma_map_2d(&maps.a_hi, A.hi, A.ld, M, A.ld, 128);
-    if (!msg) msg = tma_map_2d(&maps.a_lo, A.lo, A.ld, M, A.ld, 128);
-    if (!msg) msg = tma_map_2d(&maps.b_hi, w.hi, K, N, K, bn);
-    if (!msg) msg = tma_map_2d(&maps.b_lo, w.lo, K, N, K, bn);
+    if (!msg) msg = tma_map_2d(&maps.a_hi, A.hi, A.ld, M, A.ld, 128, kb);
+    if (!msg) msg = tma_map_2d(&maps.a_lo, A.lo, A.ld, M, A.ld, 128, kb);
+    if (!msg) msg = tma_map_2d(&maps.b_hi, w.hi, K, N, K, bn, kb);
+    if (!msg) msg = tma_map_2d(&maps.b_lo, w.lo, K, N, K, bn, kb);
     if (msg) return fail(PF_ERR_CUDA, "%s", msg);
     maps.a2_hi = maps.a_hi; maps.a2_lo = maps.a_lo;
     return launch_tma(MODE_GEMM, maps, p);
@@ -386,7 +388,7 @@ struct Fwd {
     p.c_split = A2 ? c_split : 0; p.a2_c0 = a2_c0;
     fill_epi(p, w, o, bias_gstride);
     TmaMaps maps{};
-    const int bn = tma_pick_bn(N, MODE_HALO);
+    const int bn = tma_pick_bn(N, MODE_HALO), kb = tma_pick_kb(bn, p.K);
     const char* msg = nullptr;
     if (!msg) msg = tma_map_halo(&maps.a_hi, A.hi, B, H, W, A.ld);
     if (!msg) msg = tma_map_halo(&maps.a_lo, A.lo, B, H, W, A.ld);
@@ -394,8 +396,8 @@ struct Fwd {
       if (!msg) msg = tma_map_halo(&maps.a2_hi, A2->hi, B, H, W, A2->ld);
       if (!msg) msg = tma_map_halo(&maps.a2_lo, A2->lo, B, H, W, A2->ld);
     } else { maps.a2_hi = maps.a_hi; maps.a2_lo = maps.a_lo; }
-    if (!msg) msg = tma_map_2d(&maps.b_hi, w.hi, p.K, (long long)groups * N, p.K, bn);
-    if (!msg) msg = tma_map_2d(&maps.b_lo, w.lo, p.K, (long long)groups * N, p.K, bn);
+    if (!msg) msg = tma_map_2d(&maps.b_hi, w.hi, p.K, (long long)groups * N, p.K, bn, kb);
+    if (!msg) msg = tma_map_2d(&maps.b_lo, w.lo, p.K, (long long)groups * N, p.K, bn, kb);
     if (msg) return fail(PF_ERR_CUDA, "%s", msg);
     return launch_tma(MODE_HALO, maps, p);
   }
@@ -607,7 +609,7 @@ static int run_forward(Fwd& F, const pf_batch* bt, int max_h_for_dry) {
       // x = x + mlp(norm2(x))
       TRY(F.ln(x, t1, rows, C, b.ln2, 1e-6f));
       TRY(F.linear(t1, rows, C, b.fc1, 4 * C, h1));
-      if (!dry) LAUNCHED((dwconv3x3_gelu_kernel<<<ew_grid(rows * C), 256, 0, st>>>(h1, h2, n, R, R, 4 * C, b.dw_w, b.dw_b), cudaGetLastError()));
+      if (!dry) LAUNCHED((dwconv3x3_gelu_kernel<<<ew_grid((long long)n * R * ((R + 3) / 4) * C), 256, 0, st>>>(h1, h2, n, R, R, 4 * C, b.dw_w, b.dw_b), cudaGetLastError()));
       TRY(F.linear(h2, rows, 4 * C, b.fc2, C, x, 0, x));
       F.tapf(x, rows * C, "mit.s%d.b%d", s + 1, i);
     }
@@ -655,7 +657,7 @@ static int run_forward(Fwd& F, const pf_batch* bt, int max_h_for_dry) {
       TRY(rcu_conv(o, e->rcu[lvl - 1][1][0], u, 1, nullptr, 0, nullptr));
       TRY(rcu_conv(u, e->rcu[lvl - 1][1][1], w2, 0, o, 1, nullptr));
       float* up = ar.f(px * 4 * 512);
-      if (!dry) LAUNCHED((upsample2x_kernel<<<ew_grid(px * 4 * 128), 256, 0, st>>>(w2, 512, 0, up, 512, 0, n, r, r, 512), cudaGetLastError()));
+      if (!dry) LAUNCHED((upsample2x_kernel<<<ew_grid(px * 4 * 64), 256, 0, st>>>(w2, 512, 0, up, 512, 0, n, r, r, 512), cudaGetLastError()));
       fused = up;
       F.tapf(up, px * 4 * 512, "head.fusion%d", lvl);
     }
@@ -670,7 +672,7 @@ static int run_forward(Fwd& F, const pf_batch* bt, int max_h_for_dry) {
       F.tap("head.conv0", c0, (long long)n * 160 * 160 * 128);
     }
     float* c0u = ar.f((long long)n * kNet * kNet * 128);
-    if (!dry) LAUNCHED((upsample2x_kernel<<<ew_grid((long long)n * kNet * kNet * 32), 256, 0, st>>>(c0, 128, 0, c0u, 128, 0, n, 160, 160, 128), cudaGetLastError()));
+    if (!dry) LAUNCHED((upsample2x_kernel<<<ew_grid((long long)n * kNet * kNet * 16), 256, 0, st>>>(c0, 128, 0, c0u, 128, 0, n, 160, 160, 128), cudaGetLastError()));
     {
       ConvGemmParams p = Fwd::base(c0u, 128, n, kNet, kNet, 64, 3, 1, 1, e->conv1, 32, conv1_out, 64);
       p.act = 1;
@@ -712,7 +714,7 @@ static int run_forward(Fwd& F, const pf_batch* bt, int max_h_for_dry) {
       float* h = ar.f(rows * 4 * C);
       for (int j = 0; j < kCnxDepths[s]; ++j) {
         const CnxBlockW& b = e->pn_blocks[s][j];
-        if (!dry) LAUNCHED((dwconv7x7_kernel<<<ew_grid(rows * C / 4), 256, 0, st>>>(x, y, n, r, r, C, b.dw_w, b.dw_b), cudaGetLastError()));
+        if (!dry) LAUNCHED((dwconv7x7_kernel<<<ew_grid((long long)n * r * ((r + 3) / 4) * (C / 4)), 256, 0, st>>>(x, y, n, r, r, C, b.dw_w, b.dw_b), cudaGetLastError()));
         TRY(F.ln(y, y, rows, C, b.ln, 1e-6f));
         TRY(F.linear(y, rows, C, b.pw1, 4 * C, h, 2));
         TRY(F.linear(h, rows, 4 * C, b.pw2, C, x, 0, x, b.gamma));
@@ -786,12 +788,12 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
         Epi o; o.C = kv; o.ldc = 2 * C;
         TRY(F.tgemm(t1, rows, C, 0, b.kv, 2 * C, o));
       }
-      if (!dry) LAUNCHED(attention_launch(q, kv, nullptr, n, N, C, heads, st, a));
+      if (!dry) LAUNCHED(e->use_attn_mma ? attention_mma_launch(q, kv, nullptr, n, N, C, heads, st, a) : attention_launch(q, kv, nullptr, n, N, C, heads, st, a));
       { Epi o; o.C = x; o.ldc = C; o.res = x; o.ldr = C; TRY(F.tgemm(a, rows, C, 0, b.proj, C, o)); }
       F.tapf(x, rows * C, "mit.s%d.b%d.attn", s + 1, i);
       TRY(F.ln_split(x, t1, rows, C, b.ln2, 1e-6f));
       { Epi o; o.C = h1; o.ldc = 4 * C; TRY(F.tgemm(t1, rows, C, 0, b.fc1, 4 * C, o)); }
-      if (!dry) LAUNCHED((dwconv3x3_gelu_kernel<<<ew_grid(rows * C), 256, 0, st>>>(h1, nullptr, n, R, R, 4 * C, b.dw_w, b.dw_b, h2.hi, h2.lo), cudaGetLastError()));
+      if (!dry) LAUNCHED((dwconv3x3_gelu_kernel<<<ew_grid((long long)n * R * ((R + 3) / 4) * C), 256, 0, st>>>(h1, nullptr, n, R, R, 4 * C, b.dw_w, b.dw_b, h2.hi, h2.lo), cudaGetLastError()));
       { Epi o; o.C = x; o.ldc = C; o.res = x; o.ldr = C; TRY(F.tgemm(h2, rows, 4 * C, 0, b.fc2, C, o)); }
       F.tapf(x, rows * C, "mit.s%d.b%d", s + 1, i);
     }
@@ -836,12 +838,12 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
       { Epi o; o.C = w2; o.ldc = 512; o.res = of; o.ldr = 512; o.res_relu = 1; TRY(rcu(u, e->rcu[lvl - 1][1][1], o)); }
       if (lvl > 1) {
         float* up = ar.f(px * 4 * 512);
-        if (!dry) LAUNCHED((upsample2x_kernel<<<ew_grid(px * 4 * 128), 256, 0, st>>>(w2, 512, 0, up, 512, 0, n, r, r, 512), cudaGetLastError()));
+        if (!dry) LAUNCHED((upsample2x_kernel<<<ew_grid(px * 4 * 64), 256, 0, st>>>(w2, 512, 0, up, 512, 0, n, r, r, 512), cudaGetLastError()));
         fused = up;
         F.tapf(up, px * 4 * 512, "head.fusion%d", lvl);
       } else {
         fused_s = F.salloc(px * 4, 512);
-        if (!dry) LAUNCHED((upsample2x_kernel<<<ew_grid(px * 4 * 128), 256, 0, st>>>(w2, 512, 0, nullptr, 512, 0, n, r, r, 512, fused_s.hi, fused_s.lo), cudaGetLastError()));
+        if (!dry) LAUNCHED((upsample2x_kernel<<<ew_grid(px * 4 * 64), 256, 0, st>>>(w2, 512, 0, nullptr, 512, 0, n, r, r, 512, fused_s.hi, fused_s.lo), cudaGetLastError()));
         TRY(F.tap_split("head.fusion1", fused_s, px * 4 * 512));
       }
     }
@@ -853,7 +855,7 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
       F.tap("head.conv0", c0, (long long)n * 160 * 160 * 128);
     }
     SplitT c0u = F.salloc((long long)n * kNet * kNet, 128);
-    if (!dry) LAUNCHED((upsample2x_kernel<<<ew_grid((long long)n * kNet * kNet * 32), 256, 0, st>>>(c0, 128, 0, nullptr, 128, 0, n, 160, 160, 128, c0u.hi, c0u.lo), cudaGetLastError()));
+    if (!dry) LAUNCHED((upsample2x_kernel<<<ew_grid((long long)n * kNet * kNet * 16), 256, 0, st>>>(c0, 128, 0, nullptr, 128, 0, n, 160, 160, 128, c0u.hi, c0u.lo), cudaGetLastError()));
     {
       Epi o; o.C = conv1_out; o.ldc = 64; o.c_gcoff = 32; o.act = 1;
       TRY(F.thalo(c0u, 0, 64, nullptr, 0, 0, n, kNet, kNet, 64, e->conv1, 32, 2, 32, o));
@@ -890,7 +892,7 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
       SplitT h = F.salloc(rows, 4 * C);
       for (int j = 0; j < kCnxDepths[s]; ++j) {
         const CnxBlockW& b = e->pn_blocks[s][j];
-        if (!dry) LAUNCHED((dwconv7x7_kernel<<<ew_grid(rows * C / 4), 256, 0, st>>>(x, yf, n, r, r, C, b.dw_w, b.dw_b), cudaGetLastError()));
+        if (!dry) LAUNCHED((dwconv7x7_kernel<<<ew_grid((long long)n * r * ((r + 3) / 4) * (C / 4)), 256, 0, st>>>(x, yf, n, r, r, C, b.dw_w, b.dw_b), cudaGetLastError()));
         TRY(F.ln_split(yf, y, rows, C, b.ln, 1e-6f));
         { Epi o; o.S = h; o.act = 2; TRY(F.tgemm(y, rows, C, 0, b.pw1, 4 * C, o)); }
         { Epi o; o.C = x; o.ldc = C; o.res = x; o.ldr = C; o.gamma = b.gamma; TRY(F.tgemm(h, rows, 4 * C, 0, b.pw2, C, o)); }
@@ -1010,6 +1012,7 @@ int pf_set_option(pf_handle h, const char* name, int value) {
   if (!strcmp(name, "tcgen05")) { h->use_tc = value != 0; return PF_OK; }
   if (!strcmp(name, "halo3x3")) { h->use_halo = value != 0; return PF_OK; }
   if (!strcmp(name, "tma")) { h->use_tma = value != 0; return PF_OK; }
+  if (!strcmp(name, "attn_mma")) { h->use_attn_mma = value != 0; return PF_OK; }
   return fail(PF_ERR_ARG, "pf_set_option: unknown option '%s'", name);
 }
 // out[cfg*3 + {0,1,2}] = {milliseconds, algorithmic FLOPs, launches} per GEMM engine configuration (7 configs),
@@ -1131,19 +1134,24 @@ int pf_op_attention(const float* q, const float* kv, float* out, int B, int N, i
   LAUNCHED(attention_launch(q, kv, out, B, N, C, heads, (cudaStream_t)stream));
   return PF_OK;
 }
+int pf_op_attention_mma(const float* q, const float* kv, float* out, int B, int N, int C, int heads, void* stream) {
+  if (C != heads * kAmD) return fail(PF_ERR_ARG, "pf_op_attention_mma: head_dim must be 64");
+  LAUNCHED(attention_mma_launch(q, kv, out, B, N, C, heads, (cudaStream_t)stream));
+  return PF_OK;
+}
 int pf_op_dwconv3x3_gelu(const float* x, float* y, int B, int H, int W, int C, const float* w, const float* bias, void* stream) {
   if (C % 4) return fail(PF_ERR_ARG, "C %% 4");
-  LAUNCHED((dwconv3x3_gelu_kernel<<<ew_grid((long long)B * H * W * C / 4), 256, 0, (cudaStream_t)stream>>>(x, y, B, H, W, C, w, bias), cudaGetLastError()));
+  LAUNCHED((dwconv3x3_gelu_kernel<<<ew_grid((long long)B * H * ((W + 3) / 4) * (C / 4)), 256, 0, (cudaStream_t)stream>>>(x, y, B, H, W, C, w, bias), cudaGetLastError()));
   return PF_OK;
 }
 int pf_op_dwconv7x7(const float* x, float* y, int B, int H, int W, int C, const float* w, const float* bias, void* stream) {
   if (C % 4) return fail(PF_ERR_ARG, "C %% 4");
-  LAUNCHED((dwconv7x7_kernel<<<ew_grid((long long)B * H * W * C / 4), 256, 0, (cudaStream_t)stream>>>(x, y, B, H, W, C, w, bias), cudaGetLastError()));
+  LAUNCHED((dwconv7x7_kernel<<<ew_grid((long long)B * H * ((W + 3) / 4) * (C / 4)), 256, 0, (cudaStream_t)stream>>>(x, y, B, H, W, C, w, bias), cudaGetLastError()));
   return PF_OK;
 }
 int pf_op_upsample2x(const float* x, float* y, int B, int H, int W, int C, void* stream) {
-  if (C % 4) return fail(PF_ERR_ARG, "C %% 4");
-  LAUNCHED((upsample2x_kernel<<<ew_grid((long long)B * H * W * C), 256, 0, (cudaStream_t)stream>>>(x, C, 0, y, C, 0, B, H, W, C), cudaGetLastError()));
+  if (C % 8) return fail(PF_ERR_ARG, "C %% 8");
+  LAUNCHED((upsample2x_kernel<<<ew_grid((long long)B * H * W * C / 2), 256, 0, (cudaStream_t)stream>>>(x, C, 0, y, C, 0, B, H, W, C), cudaGetLastError()));
   return PF_OK;
 }
 int pf_op_preprocess(const uint8_t* img, int H, int W, const float* mean3, const float* std3, float* y, void* stream) {

@@ -25,17 +25,19 @@ inline PFN_tensorMapEncodeTiled tma_encoder() {
   return fn;
 }
 
-// bf16 tensor [rows][ld] (row-major); box = box_rows x 32 elements (64 B), SWIZZLE_64B.  `cols` = logical row length.
-inline const char* tma_map_2d(CUtensorMap* m, const void* base, long long cols, long long rows, long long ld, int box_rows) {
+// bf16 tensor [rows][ld] (row-major); box = box_rows x kb elements (kb = 32: 64 B rows, SWIZZLE_64B; kb = 64: 128 B rows,
+// SWIZZLE_128B).  `cols` = logical row length.
+inline const char* tma_map_2d(CUtensorMap* m, const void* base, long long cols, long long rows, long long ld, int box_rows, int kb) {
   PFN_tensorMapEncodeTiled enc = tma_encoder();
   if (!enc) return "cuTensorMapEncodeTiled entry point not available";
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)kb, (cuuint32_t)box_rows};
   cuuint32_t es[2] = {1, 1};
   if (((uintptr_t)base & 15) || (strides[0] & 15) || box_rows < 1 || box_rows > 256) return "tma_map_2d: alignment / box";
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   kb == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? nullptr : "cuTensorMapEncodeTiled (2d) failed";
 }
 
@@ -61,12 +63,15 @@ inline int tma_pick_bn(int N, int mode) {
   return bn;
 }
 
-template <int BN, int MODE>
+// K elements per pipeline step: 64 for narrow tiles (BN <= 128) when K allows it, else 32
+inline int tma_pick_kb(int bn, int K) { return (bn <= 128 && K % 64 == 0) ? 64 : 32; }
+
+template <int BN, int MODE, int KB>
 inline cudaError_t gemm_tma_launch_bn(const TmaMaps& maps, const TmaGemmParams& p, int sm_count, cudaStream_t st) {
-  using Cfg = TmaCfg<BN, MODE>;
+  using Cfg = TmaCfg<BN, MODE, KB>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tma_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tma_kernel<BN, MODE, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     configured = true;
   }
@@ -74,30 +79,40 @@ inline cudaError_t gemm_tma_launch_bn(const TmaMaps& maps, const TmaGemmParams& 
   const long long m_tiles = MODE == MODE_GEMM ? cdiv(p.M, 128) : (long long)p.B * tiles_x * tiles_y;
   const long long total = m_tiles * cdiv(p.N, BN) * p.groups;
   const unsigned grid = (unsigned)(total < sm_count ? total : sm_count);
-  gemm_tma_kernel<BN, MODE><<<grid, kTmaThreads, Cfg::kSmemBytes, st>>>(maps, p, tiles_x, tiles_y);
+  // resident-weight mode (single chunk, one N tile) assumes every tile of a CTA uses the same weights: one group per launch
+  if (MODE == MODE_HALO && p.Cin == 64 && 9 * (64 / KB) <= Cfg::kStages && (p.groups > 1 || cdiv(p.N, BN) > 1)) {
+    cudaError_t last = cudaSuccess;
+    for (int g = 0; g < p.groups; ++g)
+      for (int nt = 0; nt < cdiv(p.N, BN); ++nt) {
+        TmaGemmParams q = p;     // fold group g / N tile nt into the offsets of a single-group, single-tile launch
+        q.groups = 1;
+        q.a_c0 = p.a_c0 + g * p.a_gc;
+        q.bias = p.bias ? p.bias + (long long)g * p.bias_gstride : nullptr;
+        q.c_coff = p.c_coff + g * p.c_gcoff; q.s_coff = p.s_coff + g * p.s_gcoff;
+        q.r_coff = p.r_coff + g * p.r_gcoff; q.r2_coff = p.r2_coff + g * p.r2_gcoff;
+        q.b_row0 = g * p.N;
+        if (cdiv(p.N, BN) > 1) return cudaErrorInvalidValue;   // (not needed by the network: conv_fuse_conv1 has N = 32)
+        const unsigned gr = (unsigned)(m_tiles < sm_count ? m_tiles : sm_count);
+        gemm_tma_kernel<BN, MODE, KB><<<gr, kTmaThreads, Cfg::kSmemBytes, st>>>(maps, q, tiles_x, tiles_y);
+        last = cudaGetLastError();
+        if (last != cudaSuccess) return last;
+      }
+    return last;
+  }
+  gemm_tma_kernel<BN, MODE, KB><<<grid, kTmaThreads, Cfg::kSmemBytes, st>>>(maps, p, tiles_x, tiles_y);
   return cudaGetLastError();
 }
 
-inline cudaError_t gemm_tma_launch(int mode, const TmaMaps& maps, const TmaGemmParams& p, int bn, int sm_count, cudaStream_t st) {
+inline cudaError_t gemm_tma_launch(int mode, const TmaMaps& maps, const TmaGemmParams& p, int bn, int kb, int sm_count, cudaStream_t st) {
+#define PF_TMA_CASE(BN_, MODE_, KB_) if (bn == BN_ && kb == KB_) return gemm_tma_launch_bn<BN_, MODE_, KB_>(maps, p, sm_count, st)
   if (mode == MODE_GEMM) {
-    switch (bn) {
-      case 256: return gemm_tma_launch_bn<256, MODE_GEMM>(maps, p, sm_count, st);
-      case 224: return gemm_tma_launch_bn<224, MODE_GEMM>(maps, p, sm_count, st);
-      case 192: return gemm_tma_launch_bn<192, MODE_GEMM>(maps, p, sm_count, st);
-      case 160: return gemm_tma_launch_bn<160, MODE_GEMM>(maps, p, sm_count, st);
-      case 128: return gemm_tma_launch_bn<128, MODE_GEMM>(maps, p, sm_count, st);
-      case 96: return gemm_tma_launch_bn<96, MODE_GEMM>(maps, p, sm_count, st);
-      case 64: return gemm_tma_launch_bn<64, MODE_GEMM>(maps, p, sm_count, st);
-      case 32: return gemm_tma_launch_bn<32, MODE_GEMM>(maps, p, sm_count, st);
-    }
+    PF_TMA_CASE(256, MODE_GEMM, 32); PF_TMA_CASE(224, MODE_GEMM, 32); PF_TMA_CASE(192, MODE_GEMM, 32); PF_TMA_CASE(160, MODE_GEMM, 32);
+    PF_TMA_CASE(128, MODE_GEMM, 32); PF_TMA_CASE(96, MODE_GEMM, 32); PF_TMA_CASE(64, MODE_GEMM, 32); PF_TMA_CASE(32, MODE_GEMM, 32);
+    PF_TMA_CASE(128, MODE_GEMM, 64); PF_TMA_CASE(96, MODE_GEMM, 64); PF_TMA_CASE(64, MODE_GEMM, 64); PF_TMA_CASE(32, MODE_GEMM, 64);
   } else {
-    switch (bn) {
-      case 256: return gemm_tma_launch_bn<256, MODE_HALO>(maps, p, sm_count, st);
-      case 128: return gemm_tma_launch_bn<128, MODE_HALO>(maps, p, sm_count, st);
-      case 64: return gemm_tma_launch_bn<64, MODE_HALO>(maps, p, sm_count, st);
-      case 32: return gemm_tma_launch_bn<32, MODE_HALO>(maps, p, sm_count, st);
-    }
+    PF_TMA_CASE(256, MODE_HALO, 32); PF_TMA_CASE(128, MODE_HALO, 64); PF_TMA_CASE(64, MODE_HALO, 64); PF_TMA_CASE(32, MODE_HALO, 64);
   }
+#undef PF_TMA_CASE
   return cudaErrorInvalidValue;
 }
 
