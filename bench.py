@@ -46,15 +46,12 @@ def parse():
 
 
 class ClockSampler:
-    """SM clock / throttle-reason samples during the timed region (B200_PROFILING.md recipe), read through NVML in a
-    background thread every 50 ms (an `nvidia-smi -lms 100` child process measurably slowed the launches it was observing);
-    falls back to one nvidia-smi query per second when pynvml is unavailable."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle-reason samples DURING the timed region (B200_PROFILING.md recipe), read through NVML from the
+    main thread right after each step has been enqueued (the GPU is then busy with that step and the host is far ahead of it).
+    A concurrent poller -- an `nvidia-smi -lms` child or an NVML thread -- measurably slowed the launches it was observing."""
 
     def __init__(self, index):
-        self.index, self.rows, self.active, self.stop_flag = index, [], False, False
-        self.nvml = None
+        self.index, self.rows, self.nvml = index, [], None
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -63,45 +60,30 @@ class ClockSampler:
             self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
         except Exception:
             self.nvml = None
-        self.t = threading.Thread(target=self._run, daemon=True)
-        self.t.start()
 
-    def _sample(self):
-        if self.nvml is not None:
-            n = self.nvml
-            sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
-            try:
-                r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-            except Exception:
-                r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-            reasons = []
-            for name, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40)):
-                if r & bit:
-                    reasons.append(name)
-            return sm, self.max_sm, reasons
-        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                             capture_output=True, text=True).stdout.strip().split(",")
-        c = [x.strip() for x in out]
-        reasons = [nm for nm, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[3:7]) if v.lower().startswith("active")]
-        return float(c[0]), float(c[1]), reasons
-
-    def _run(self):
-        period = 0.05 if self.nvml is not None else 1.0
-        while not self.stop_flag:
-            if self.active:
+    def sample(self):
+        try:
+            if self.nvml is not None:
+                n = self.nvml
+                sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
                 try:
-                    self.rows.append(self._sample())
+                    r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 except Exception:
-                    pass
-            time.sleep(period)
+                    r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                reasons = [name for name, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20),
+                                                  ("hw_thermal_slowdown", 0x40)) if r & bit]
+                self.rows.append((sm, self.max_sm, reasons))
+            else:
+                q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                     "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+                c = [x.strip() for x in subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                                       capture_output=True, text=True).stdout.strip().split(",")]
+                reasons = [nm for nm, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[2:6]) if v.lower().startswith("active")]
+                self.rows.append((float(c[0]), float(c[1]), reasons))
+        except Exception:
+            pass
 
     def stop(self):
-        if self.active or not self.rows:
-            try:
-                self.rows.append(self._sample())   # at least one sample, taken while the last step is still draining
-            except Exception:
-                pass
-        self.stop_flag = True
         sm = sorted(r[0] for r in self.rows)
         reasons = sorted({x for r in self.rows for x in r[2]})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.rows[0][1] if self.rows else None, "reasons": reasons,
@@ -203,20 +185,15 @@ def main():
         eng.forward(B, heights, widths, blob=blob, offsets=offsets)
     barrier()
     sampler = ClockSampler(local)
-    time.sleep(0.3)
     launches0 = L.pf_kernel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler.active = True
     e0.record()
     for _ in range(args.steps):
         flush.fill_(1)  # L2 flush between timed iterations (inside the timed region: ~0.1 ms of ~30)
         out = eng.forward(B, heights, widths, blob=blob, offsets=offsets)
+        sampler.sample()   # this step is now executing (or queued) on the GPU
     e1.record()
-    clocks_tail = sampler._sample() if sampler.nvml is not None else None   # GPU still busy: the steps are queued behind us
-    if clocks_tail:
-        sampler.rows.append(clocks_tail)
     barrier()
-    sampler.active = False
     ms = e0.elapsed_time(e1)
     launches = L.pf_kernel_launch_count() - launches0
     clocks = sampler.stop()

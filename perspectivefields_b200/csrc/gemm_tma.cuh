@@ -12,7 +12,8 @@
 //               tools/tc_probe.cu).  Weights stream through an NS-stage ring of 32-wide K steps (2 per tap and chunk).
 //
 //   warp 0 : TMA producer (B ring; in MODE_GEMM also A)      warp 2 : TMEM allocator, MODE_HALO halo (A) producer
-//   warp 1 : MMA issuer (one elected lane)                   warps 4-7 : epilogue (TMEM lane quarter = warp % 4)
+//   warp 1 : MMA issuer (one elected lane)                   warps 4-11: epilogue (TMEM lane quarter = warp % 4, two warps per
+//                                                                        quarter draining alternate 32-column chunks)
 //   two TMEM accumulators (2 x BN columns): the epilogue of tile i runs under the main loop of tile i+1.
 //
 // Epilogue (fused): + bias | border-class bias, ReLU / GELU, layer scale, + relu?(residual), + second residual; writes the
@@ -25,7 +26,7 @@
 namespace pf {
 
 constexpr int MODE_GEMM = 0, MODE_HALO = 1;
-constexpr int kTmaThreads = 256;
+constexpr int kTmaThreads = 384;   // warps 0-3: TMA / MMA / TMEM-alloc+halo / idle;  warps 4-11: epilogue (two per TMEM lane quarter)
 constexpr int kHaloBytes = 180 * 128;   // one bf16 plane of an 18 x 10 pixel x 64 channel halo (what one TMA box delivers)
 
 struct TmaGemmParams {
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.a_hi); tma_prefetch_desc(&maps.a_lo); tma_prefetch_desc(&maps.b_hi); tma_prefetch_desc(&maps.b_lo);
     for (int s = 0; s < NS; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(full_a(i), 1); mbar_init(empty_a(i), 1); mbar_init(tmem_full(i), 1); mbar_init(tmem_empty(i), 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(full_a(i), 1); mbar_init(empty_a(i), 1); mbar_init(tmem_full(i), 1); mbar_init(tmem_empty(i), 256); }
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
@@ -246,7 +247,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
     }
   } else if (warp >= 4) {
     // ======================================================================= epilogue warps
-    const int q = warp - 4;                       // TMEM lane quarter
+    const int q = warp & 3;                       // TMEM lane quarter (hardware: warp id % 4)
+    const int eh = (warp - 4) >> 2;               // which half of the 32-column chunks this warp drains
     const int r = q * 32 + lane;                  // row of the tile
     int tl = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
@@ -274,10 +276,12 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
       mbar_wait(tmem_full(as), (tl >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
+      for (int ch = eh; ch < BN / 32; ch += 2) {
         uint32_t v[32];
+        if (p.act & 0x200) continue;                       // (probe) no TMEM read, no stores
         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + ch * 32), v);
         const int nb = n0 + ch * 32;
+        if (p.act & 0x100) { if (v[0] == 0x12345678u && p.C) p.C[0] = 1.f; continue; }   // (probe) TMEM read only
         if (valid && nb < p.N) {
           float o[32];
 #pragma unroll
