@@ -55,10 +55,14 @@ template <int BN, int MODE, int KB> struct TmaCfg {
   static constexpr int kAPlane = 128 * KB * 2;                  // MODE_GEMM: plane of a 128 x KB A tile
   static constexpr int kStage = (MODE == MODE_GEMM ? 2 * kAPlane : 0) + 2 * kBPlane;
   static constexpr int kABuf = 2 * kHtPlaneBytes;               // MODE_HALO: hi + lo halo planes (1024 B multiples)
-  static constexpr int kBudget = 225 * 1024 - (MODE == MODE_HALO ? 2 * kABuf : 0);
+  // MODE_GEMM epilogue staging: per epilogue warp 2 x 4 KB output tiles (32 rows x 32 columns fp32, or bf16 hi + lo) for the
+  // TMA stores and 2 x 4 KB residual tiles filled by TMA loads; plus bias / layer-scale copies (2 x BN floats per warp).
+  static constexpr int kEpiStage = MODE == MODE_GEMM ? 4 * 16384 : 0;
+  static constexpr int kEpiVec = MODE == MODE_GEMM ? 4 * 2 * 256 * 4 : 0;
+  static constexpr int kBudget = 225 * 1024 - kEpiStage - kEpiVec - (MODE == MODE_HALO ? 2 * kABuf : 0);
   static constexpr int kStagesRaw = kBudget / kStage;
   static constexpr int kStages = kStagesRaw > 16 ? 16 : kStagesRaw;
-  static constexpr int kSmemBytes = (MODE == MODE_HALO ? 2 * kABuf : 0) + kStages * kStage + 512 + 1024;
+  static constexpr int kSmemBytes = (MODE == MODE_HALO ? 2 * kABuf : 0) + kStages * kStage + kEpiStage + kEpiVec + 512 + 1024;
   static constexpr int kTmemCols = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
   static constexpr uint32_t kIdesc = TcCfg<BN>::kIdesc;
   static_assert(kStages >= 3, "ring too shallow");
@@ -89,8 +93,18 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+
 struct TmaMaps {   // passed by value as a __grid_constant__ kernel parameter
   CUtensorMap a_hi, a_lo, a2_hi, a2_lo, b_hi, b_lo;
+  CUtensorMap c, s_hi, s_lo, res;   // MODE_GEMM epilogue: fp32 output, split output planes, fp32 residual (32 x 32 boxes)
 };
 
 template <int BN, int MODE, int KB>
@@ -104,7 +118,9 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
   unsigned char* sm = smem_dyn + (sbase - raw);
   const uint32_t a_base = sbase;                                                  // MODE_HALO: 2 halo buffers
   const uint32_t ring = sbase + (MODE == MODE_HALO ? 2 * Cfg::kABuf : 0);         // NS stages
-  const uint32_t bars = ring + NS * Cfg::kStage;
+  const uint32_t epi_base = ring + NS * Cfg::kStage;                              // MODE_GEMM: 4 x 16 KB staging (1024 B aligned)
+  const uint32_t vec_base = epi_base + Cfg::kEpiStage;                            // MODE_GEMM: bias / gamma copies
+  const uint32_t bars = vec_base + Cfg::kEpiVec;
   auto full_b = [&](int s) { return bars + 8u * s; };
   auto empty_b = [&](int s) { return bars + 8u * (NS + s); };
   auto full_a = [&](int i) { return bars + 8u * (2 * NS + i); };
@@ -112,6 +128,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
   auto tmem_full = [&](int i) { return bars + 8u * (2 * NS + 4 + i); };
   auto tmem_empty = [&](int i) { return bars + 8u * (2 * NS + 6 + i); };
   const uint32_t tmem_slot = bars + 8u * (2 * NS + 8);
+  auto res_bar = [&](int q, int i) { return bars + 8u * (2 * NS + 9 + 2 * q + i); };   // MODE_GEMM: residual tiles landed
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_tiles = cdiv(p.N, BN);
@@ -126,7 +143,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.a_hi); tma_prefetch_desc(&maps.a_lo); tma_prefetch_desc(&maps.b_hi); tma_prefetch_desc(&maps.b_lo);
     for (int s = 0; s < NS; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(full_a(i), 1); mbar_init(empty_a(i), 1); mbar_init(tmem_full(i), 1); mbar_init(tmem_empty(i), 256); }
+    for (int i = 0; i < 2; ++i) { mbar_init(full_a(i), 1); mbar_init(empty_a(i), 1); mbar_init(tmem_full(i), 1); mbar_init(tmem_empty(i), MODE == MODE_GEMM ? 128 : 256); }
+    for (int i = 0; i < 8; ++i) mbar_init(res_bar(i >> 1, i & 1), 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
@@ -245,8 +263,126 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
         if (MODE == MODE_HALO && chunk_end) ++ita;
       }
     }
+  } else if (MODE == MODE_GEMM && warp >= 4) {
+    // ======================================================================= MODE_GEMM epilogue: warps 4-7, TMA stores
+    // Per warp (32 tile rows) and 32-column chunk: TMEM -> registers, + bias, activation, layer scale, + residual tile (TMA-
+    // loaded into swizzled smem one chunk ahead), then the result goes to a swizzled smem tile and ONE thread issues a
+    // bulk-tensor store: global traffic is full 128 B rows written by the copy engine instead of 16 B-per-row thread stores.
+    if (warp < 8) {
+      const int q = warp & 3;
+      const uint32_t stg = epi_base + q * 16384;            // out[2] at +0, +4096 ; res[2] at +8192, +12288
+      unsigned char* stg_p = sm + (stg - sbase);
+      float* bias_s = reinterpret_cast<float*>(sm + (vec_base - sbase)) + q * 512;
+      float* gamma_s = bias_s + 256;
+      const bool has_res = p.res != nullptr;
+      uint32_t rl = 0, rc = 0;                              // residual tiles requested / consumed by this warp
+      uint32_t oc = 0;                                      // output tiles staged so far (buffer = oc & 1, across tiles)
+      int tl = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+        int mt, g, n0;
+        decode(tile, mt, g, n0);
+        const int as = tl & 1;
+        const int row0 = mt * 128 + q * 32;
+        const int nch = ((p.N - n0 < BN ? p.N - n0 : BN) + 31) / 32;
+        for (int j = lane; j < BN; j += 32) {
+          const bool ok = n0 + j < p.N;
+          bias_s[j] = (p.bias_mode && ok) ? __ldg(p.bias + n0 + j) : 0.f;
+          gamma_s[j] = (p.gamma && ok) ? __ldg(p.gamma + n0 + j) : 1.f;
+        }
+        __syncwarp();
+        const bool warp_active = row0 < p.M && nch > 0;      // warp-uniform: this warp's 32 rows intersect the matrix
+        if (has_res && warp_active) {
+          if (lane == 0) {
+            mbar_expect_tx(res_bar(q, rl & 1), 4096);
+            tma_load_2d(stg + 8192 + (rl & 1) * 4096, &maps.res, res_bar(q, rl & 1), p.r_coff + n0, row0);
+          }
+          ++rl;
+        }
+        mbar_wait(tmem_full(as), (tl >> 1) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int ch = 0; ch < nch; ++ch) {
+          uint32_t v[32];
+          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + ch * 32), v);
+          if (!warp_active) continue;                                  // whole warp beyond the matrix (warp-uniform)
+          const int ob = oc & 1;
+          ++oc;
+          if (has_res && ch + 1 < nch) {                               // residual tile of the next chunk
+            if (lane == 0) {
+              mbar_expect_tx(res_bar(q, rl & 1), 4096);
+              tma_load_2d(stg + 8192 + (rl & 1) * 4096, &maps.res, res_bar(q, rl & 1), p.r_coff + n0 + (ch + 1) * 32, row0);
+            }
+            ++rl;
+          }
+          if (lane == 0) bulk_wait_read<1>();                          // the store that used out[ob] two chunks ago has read it
+          __syncwarp();
+          float o[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bv = *reinterpret_cast<const float4*>(bias_s + ch * 32 + j);
+            o[j] = __uint_as_float(v[j]) + bv.x; o[j + 1] = __uint_as_float(v[j + 1]) + bv.y;
+            o[j + 2] = __uint_as_float(v[j + 2]) + bv.z; o[j + 3] = __uint_as_float(v[j + 3]) + bv.w;
+          }
+          if (p.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], 0.f);
+          } else if (p.act == 2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = gelu_erf(o[j]);
+          }
+          if (p.gamma) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 gv = *reinterpret_cast<const float4*>(gamma_s + ch * 32 + j);
+              o[j] *= gv.x; o[j + 1] *= gv.y; o[j + 2] *= gv.z; o[j + 3] *= gv.w;
+            }
+          }
+          if (has_res) {
+            mbar_wait(res_bar(q, rc & 1), (rc >> 1) & 1);
+            const unsigned char* rb = stg_p + 8192 + (rc & 1) * 4096 + lane * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 rv = *reinterpret_cast<const float4*>(rb + ((j ^ (lane & 7)) << 4));
+              if (p.res_relu) { rv.x = fmaxf(rv.x, 0.f); rv.y = fmaxf(rv.y, 0.f); rv.z = fmaxf(rv.z, 0.f); rv.w = fmaxf(rv.w, 0.f); }
+              o[4 * j] += rv.x; o[4 * j + 1] += rv.y; o[4 * j + 2] += rv.z; o[4 * j + 3] += rv.w;
+            }
+            ++rc;
+          }
+          unsigned char* ob_p = stg_p + ob * 4096;
+          if (p.C) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(ob_p + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          } else {   // split output only: hi plane tile at +0, lo plane tile at +2048, rows of 64 B, SWIZZLE_64B
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 h, l;
+              float t[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) t[e] = p.split_relu ? fmaxf(o[8 * j + e], 0.f) : o[8 * j + e];
+              split_bf16x2(t[0], t[1], h.x, l.x); split_bf16x2(t[2], t[3], h.y, l.y);
+              split_bf16x2(t[4], t[5], h.z, l.z); split_bf16x2(t[6], t[7], h.w, l.w);
+              const int off = lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4);
+              *reinterpret_cast<uint4*>(ob_p + off) = h;
+              *reinterpret_cast<uint4*>(ob_p + 2048 + off) = l;
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            const int col = n0 + ch * 32;
+            if (p.C) tma_store_2d(&maps.c, stg + ob * 4096, p.c_coff + col, row0);
+            else { tma_store_2d(&maps.s_hi, stg + ob * 4096, p.s_coff + col, row0); tma_store_2d(&maps.s_lo, stg + ob * 4096 + 2048, p.s_coff + col, row0); }
+            bulk_commit();
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(tmem_empty(as));
+      }
+      if (lane == 0) bulk_wait_all();            // all stores have landed before the CTA exits
+    }
   } else if (warp >= 4) {
-    // ======================================================================= epilogue warps
+    // ======================================================================= epilogue warps (MODE_HALO)
     const int q = warp & 3;                       // TMEM lane quarter (hardware: warp id % 4)
     const int eh = (warp - 4) >> 2;               // which half of the 32-column chunks this warp drains
     const int r = q * 32 + lane;                  // row of the tile

@@ -324,7 +324,7 @@ struct Fwd {
     return PF_OK;
   }
   int launch_tma(int mode, const TmaMaps& maps, const TmaGemmParams& p) {
-    const int bn = tma_pick_bn(p.N, mode), kb = tma_pick_kb(bn, p.K);
+    const int bn = tma_pick_bn(p.N, mode), kb = tma_pick_kb(bn, p.K, mode);
     if (e->profile) {
       pf_engine::ProfRec r{};
       for (cudaEvent_t* ev : {&r.a, &r.b}) {
@@ -368,14 +368,24 @@ struct Fwd {
     p.M = (int)M; p.Cin = K; p.N = N; p.K = K; p.a_c0 = a_c0; p.groups = 1;
     fill_epi(p, w, o, 0);
     TmaMaps maps{};
-    const int bn = tma_pick_bn(N, MODE_GEMM), kb = tma_pick_kb(bn, K);
+    const int bn = tma_pick_bn(N, MODE_GEMM), kb = tma_pick_kb(bn, K, MODE_GEMM);
     const char* msg = nullptr;
     if (!msg) msg = tma_map_2d(&maps.a_hi, A.hi, A.ld, M, A.ld, 128, kb);
     if (!msg) msg = tma_map_2d(&maps.a_lo, A.lo, A.ld, M, A.ld, 128, kb);
     if (!msg) msg = tma_map_2d(&maps.b_hi, w.hi, K, N, K, bn, kb);
     if (!msg) msg = tma_map_2d(&maps.b_lo, w.lo, K, N, K, bn, kb);
+    // epilogue tiles go through TMA as well: fp32 output, or (when there is no fp32 output) the split planes; residual
+    if (o.C && o.S.hi) return fail(PF_ERR_ARG, "tgemm: fp32 and split outputs together are not supported in GEMM mode");
+    if (o.res2 || o.bias_mode == 2) return fail(PF_ERR_ARG, "tgemm: second residual / border-class bias are halo-mode features");
+    if (!msg && o.C) msg = tma_map_tile32(&maps.c, o.C, M, o.ldc, true);
+    if (!msg && o.S.hi) msg = tma_map_tile32(&maps.s_hi, o.S.hi, M, o.S.ld, false);
+    if (!msg && o.S.hi) msg = tma_map_tile32(&maps.s_lo, o.S.lo, M, o.S.ld, false);
+    if (!msg && o.res) msg = tma_map_tile32(&maps.res, o.res, M, o.ldr, true);
     if (msg) return fail(PF_ERR_CUDA, "%s", msg);
     maps.a2_hi = maps.a_hi; maps.a2_lo = maps.a_lo;
+    if (!o.C) maps.c = maps.a_hi;
+    if (!o.S.hi) { maps.s_hi = maps.a_hi; maps.s_lo = maps.a_hi; }
+    if (!o.res) maps.res = maps.a_hi;
     return launch_tma(MODE_GEMM, maps, p);
   }
   // 3x3 / stride 1 / pad 1 convolution on split NHWC planes (optionally a second source for channels >= c_split)
@@ -388,7 +398,7 @@ struct Fwd {
     p.c_split = A2 ? c_split : 0; p.a2_c0 = a2_c0;
     fill_epi(p, w, o, bias_gstride);
     TmaMaps maps{};
-    const int bn = tma_pick_bn(N, MODE_HALO), kb = tma_pick_kb(bn, p.K);
+    const int bn = tma_pick_bn(N, MODE_HALO), kb = tma_pick_kb(bn, p.K, MODE_HALO);
     const char* msg = nullptr;
     if (!msg) msg = tma_map_halo(&maps.a_hi, A.hi, B, H, W, A.ld);
     if (!msg) msg = tma_map_halo(&maps.a_lo, A.lo, B, H, W, A.ld);
@@ -396,6 +406,7 @@ struct Fwd {
       if (!msg) msg = tma_map_halo(&maps.a2_hi, A2->hi, B, H, W, A2->ld);
       if (!msg) msg = tma_map_halo(&maps.a2_lo, A2->lo, B, H, W, A2->ld);
     } else { maps.a2_hi = maps.a_hi; maps.a2_lo = maps.a_lo; }
+    maps.c = maps.a_hi; maps.s_hi = maps.a_hi; maps.s_lo = maps.a_hi; maps.res = maps.a_hi;   // halo mode: epilogue stores from registers
     if (!msg) msg = tma_map_2d(&maps.b_hi, w.hi, p.K, (long long)groups * N, p.K, bn, kb);
     if (!msg) msg = tma_map_2d(&maps.b_lo, w.lo, p.K, (long long)groups * N, p.K, bn, kb);
     if (msg) return fail(PF_ERR_CUDA, "%s", msg);

@@ -41,6 +41,22 @@ inline const char* tma_map_2d(CUtensorMap* m, const void* base, long long cols, 
   return r == CUDA_SUCCESS ? nullptr : "cuTensorMapEncodeTiled (2d) failed";
 }
 
+// 32-row x 32-column epilogue tile of a row-major [rows][ld] tensor: fp32 (128 B rows, SWIZZLE_128B) or bf16 (64 B, SWIZZLE_64B)
+inline const char* tma_map_tile32(CUtensorMap* m, const void* base, long long rows, long long ld, bool is_f32) {
+  PFN_tensorMapEncodeTiled enc = tma_encoder();
+  if (!enc) return "cuTensorMapEncodeTiled entry point not available";
+  const int es_bytes = is_f32 ? 4 : 2;
+  cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * es_bytes};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t es[2] = {1, 1};
+  if (((uintptr_t)base & 15) || (strides[0] & 15)) return "tma_map_tile32: alignment";
+  CUresult r = enc(m, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, is_f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? nullptr : "cuTensorMapEncodeTiled (tile32) failed";
+}
+
 // bf16 NHWC tensor [B][H][W][ld]; box = 1 x 18 x 10 x 64 channels (128 B), SWIZZLE_128B: one halo chunk.
 inline const char* tma_map_halo(CUtensorMap* m, const void* base, int B, int H, int W, int ld) {
   PFN_tensorMapEncodeTiled enc = tma_encoder();
@@ -63,8 +79,9 @@ inline int tma_pick_bn(int N, int mode) {
   return bn;
 }
 
-// K elements per pipeline step: 64 for narrow tiles (BN <= 128) when K allows it, else 32
-inline int tma_pick_kb(int bn, int K) { return (bn <= 128 && K % 64 == 0) ? 64 : 32; }
+// K elements per pipeline step: 64 for narrow tiles when K allows it (halo mode: BN <= 128; GEMM mode, whose stages also
+// hold the A tile and whose epilogue staging takes 72 KB: BN <= 64), else 32
+inline int tma_pick_kb(int bn, int K, int mode) { return (bn <= (mode == MODE_HALO ? 128 : 64) && K % 64 == 0) ? 64 : 32; }
 
 template <int BN, int MODE, int KB>
 inline cudaError_t gemm_tma_launch_bn(const TmaMaps& maps, const TmaGemmParams& p, int sm_count, cudaStream_t st) {
@@ -108,7 +125,7 @@ inline cudaError_t gemm_tma_launch(int mode, const TmaMaps& maps, const TmaGemmP
   if (mode == MODE_GEMM) {
     PF_TMA_CASE(256, MODE_GEMM, 32); PF_TMA_CASE(224, MODE_GEMM, 32); PF_TMA_CASE(192, MODE_GEMM, 32); PF_TMA_CASE(160, MODE_GEMM, 32);
     PF_TMA_CASE(128, MODE_GEMM, 32); PF_TMA_CASE(96, MODE_GEMM, 32); PF_TMA_CASE(64, MODE_GEMM, 32); PF_TMA_CASE(32, MODE_GEMM, 32);
-    PF_TMA_CASE(128, MODE_GEMM, 64); PF_TMA_CASE(96, MODE_GEMM, 64); PF_TMA_CASE(64, MODE_GEMM, 64); PF_TMA_CASE(32, MODE_GEMM, 64);
+    PF_TMA_CASE(64, MODE_GEMM, 64); PF_TMA_CASE(32, MODE_GEMM, 64);
   } else {
     PF_TMA_CASE(256, MODE_HALO, 32); PF_TMA_CASE(128, MODE_HALO, 64); PF_TMA_CASE(64, MODE_HALO, 64); PF_TMA_CASE(32, MODE_HALO, 64);
   }
