@@ -90,6 +90,19 @@ class ClockSampler:
                 "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
+def physical_cores():
+    """Threads for the CPU reference: one per physical core (torch's own default when OMP_NUM_THREADS is unset).  Using every
+    hyper-thread (128 on this pool's hosts) makes ATen's CPU kernels ~10x SLOWER, which would only flatter the GPU number."""
+    try:
+        import psutil
+        n = psutil.cpu_count(logical=False)
+        if n:
+            return int(n)
+    except Exception:
+        pass
+    return max(1, (os.cpu_count() or 2) // 2)
+
+
 def cpu_reference_images_per_s(n_images, repeats, threads=None):
     """The reference algorithm (oracle port, oracle/model.py == reference ATen calls) on the host cores."""
     import torch
@@ -97,8 +110,7 @@ def cpu_reference_images_per_s(n_images, repeats, threads=None):
     from oracle import model as om
     from oracle import weights_gen as wg
 
-    if threads:
-        torch.set_num_threads(threads)
+    torch.set_num_threads(threads or physical_cores())
     sd = wg.synth_state_dict(VERSION, 0)
     imgs = wg.synth_images(n_images, H, W, 0)
     om.inference_batch(sd, VERSION, imgs[:1])  # warm-up
@@ -113,7 +125,7 @@ def cpu_reference_images_per_s(n_images, repeats, threads=None):
 
 def run_reference(args, rank):
     """--impl reference: the reference's CPU implementation of the path (the oracle port: the reference is pure Python
-    and /root/reference does not exist on the GPU box) on all host cores; each step = inference_batch of a bounded
+    and /root/reference does not exist on the GPU box) on all physical host cores; each step = inference_batch of a bounded
     sample of the workload."""
     if rank != 0:
         return
@@ -122,8 +134,7 @@ def run_reference(args, rank):
     from oracle import model as om
     from oracle import weights_gen as wg
 
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    torch.set_num_threads(physical_cores())     # torchrun exports OMP_NUM_THREADS=1: set the pool size explicitly
     sd = wg.synth_state_dict(VERSION, 0)
     n = args.cpu_sample
     imgs = wg.synth_images(n, H, W, 0)
@@ -188,11 +199,16 @@ def main():
     launches0 = L.pf_kernel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    host_t0 = time.perf_counter()
+    host_fwd = 0.0
     for _ in range(args.steps):
         flush.fill_(1)  # L2 flush between timed iterations (inside the timed region: ~0.1 ms of ~30)
+        h0 = time.perf_counter()
         out = eng.forward(B, heights, widths, blob=blob, offsets=offsets)
+        host_fwd += time.perf_counter() - h0
         sampler.sample()   # this step is now executing (or queued) on the GPU
     e1.record()
+    host_enqueue_ms = (time.perf_counter() - host_t0) * 1000 / args.steps
     barrier()
     ms = e0.elapsed_time(e1)
     launches = L.pf_kernel_launch_count() - launches0
@@ -288,7 +304,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, threads = cpu_reference_images_per_s(args.cpu_sample, 3)
         cpu = {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
-               "sample": f"inference_batch of {args.cpu_sample} of the workload's 640x480 images, median of 3, torch CPU fp32, host has {os.cpu_count()} logical cores"}
+               "sample": f"inference_batch of {args.cpu_sample} of the workload's 640x480 images, median of 3, torch CPU fp32, one thread per physical core (host has {os.cpu_count()} logical cores)"}
 
     if rank == 0:
         print(json.dumps({
@@ -301,6 +317,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
             "gpu_launches": int(launches),
+            "host_enqueue_ms_per_step": host_enqueue_ms, "host_pf_forward_ms_per_step": host_fwd * 1000 / args.steps,
             "roofline": roofline,
             "cpu_baseline": cpu,
         }), flush=True)

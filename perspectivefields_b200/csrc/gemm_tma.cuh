@@ -244,16 +244,19 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
         if (!b_resident || tl == 0) mbar_wait(full_b(sb), b_resident ? 0 : ((it / NS) & 1));
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t b_hi = ring + sb * Cfg::kStage + (MODE == MODE_GEMM ? 2 * Cfg::kAPlane : 0), b_lo = b_hi + Cfg::kBPlane;
+          const uint32_t b_hi = ring + sb * Cfg::kStage + (MODE == MODE_GEMM ? 2 * Cfg::kAPlane : 0);
+          // descriptors of this step's first K=16 slice; the following slices are +32 B, i.e. +2 in the (address >> 4) field
+          // (no carry: shared-memory addresses are < 2^18), so the issuing thread spends two adds per MMA instead of a rebuild
+          uint64_t dah = MODE == MODE_HALO ? ht_a_desc(a_hi + a_kbase) : tma_tile_desc<KB>(a_hi);
+          uint64_t dal = dah + (uint64_t)((a_lo - a_hi) >> 4);
+          uint64_t dbh = tma_tile_desc<KB>(b_hi);
+          uint64_t dbl = dbh + (uint64_t)(Cfg::kBPlane >> 4);
 #pragma unroll
           for (int kk = 0; kk < KB / 16; ++kk) {
-            uint64_t dah, dal;
-            if (MODE == MODE_HALO) { dah = ht_a_desc(a_hi + a_kbase + kk * 32); dal = ht_a_desc(a_lo + a_kbase + kk * 32); }
-            else { dah = tma_tile_desc<KB>(a_hi + kk * 32); dal = tma_tile_desc<KB>(a_lo + kk * 32); }
-            const uint64_t dbh = tma_tile_desc<KB>(b_hi + kk * 32), dbl = tma_tile_desc<KB>(b_lo + kk * 32);
             umma_bf16(acc, dal, dbh, Cfg::kIdesc, (kc | kk) ? 1u : 0u);
             umma_bf16(acc, dah, dbl, Cfg::kIdesc, 1u);
             umma_bf16(acc, dah, dbh, Cfg::kIdesc, 1u);
+            dah += 2; dal += 2; dbh += 2; dbl += 2;
           }
           if (!b_resident) umma_commit(empty_b(s));
           if (MODE == MODE_HALO && chunk_end) umma_commit(empty_a(ita & 1));

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <functional>
 #include <unordered_map>
 #include <vector>
 
@@ -111,6 +112,20 @@ struct pf_engine {
   struct DevTable { int ksize; int* bounds; int* coeffs; };
   std::map<int, DevTable> tables;
   // per-launch profiling of the GEMM engine (bench.py roofline leg): CUDA events on the launch stream
+  // tensor maps are pure functions of (pointer, shape, box): cached across calls (the arena hands out the same addresses for the
+  // same batch size), which takes cuTensorMapEncodeTiled (~5 us each, ~1800 per forward) off the launch path
+  struct MapKey {
+    const void* base; long long d0, d1, d2; int kind, box, kb;
+    bool operator==(const MapKey& o) const { return base == o.base && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && kind == o.kind && box == o.box && kb == o.kb; }
+  };
+  struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+      size_t h = std::hash<const void*>()(k.base);
+      for (long long v : {k.d0, k.d1, k.d2, (long long)k.kind, (long long)k.box, (long long)k.kb}) h = h * 1000003u ^ std::hash<long long>()(v);
+      return h;
+    }
+  };
+  std::unordered_map<MapKey, CUtensorMap, MapKeyHash> map_cache;
   bool use_attn_mma = true;   // tensor-core attention core (option "attn_mma"; 0 = CUDA-core fp32 kernel)
   bool use_tma = true;   // whole forward on the TMA -> tcgen05 engine with pre-split activations (option "tma"; 0 = legacy engines)
   int sm_count = 148;
@@ -360,6 +375,27 @@ struct Fwd {
     p.C = o.C; p.ldc = o.ldc; p.c_coff = o.c_coff; p.c_gcoff = o.c_gcoff;
     p.Shi = o.S.hi; p.Slo = o.S.lo; p.lds = o.S.ld; p.s_coff = o.s_coff; p.s_gcoff = o.s_gcoff; p.split_relu = o.split_relu;
   }
+  // cached tensor-map constructors
+  template <class F>
+  const char* cached_map(CUtensorMap* out, const pf_engine::MapKey& key, F&& make) {
+    auto it = e->map_cache.find(key);
+    if (it != e->map_cache.end()) { *out = it->second; return nullptr; }
+    const char* msg = make(out);
+    if (!msg) {
+      if (e->map_cache.size() > 20000) e->map_cache.clear();
+      e->map_cache.emplace(key, *out);
+    }
+    return msg;
+  }
+  const char* map2d(CUtensorMap* m, const void* base, long long cols, long long rows, long long ld, int box_rows, int kb) {
+    return cached_map(m, pf_engine::MapKey{base, cols, rows, ld, 0, box_rows, kb}, [&](CUtensorMap* o) { return tma_map_2d(o, base, cols, rows, ld, box_rows, kb); });
+  }
+  const char* map_tile32(CUtensorMap* m, const void* base, long long rows, long long ld, bool f32) {
+    return cached_map(m, pf_engine::MapKey{base, rows, ld, 0, f32 ? 1 : 2, 32, 0}, [&](CUtensorMap* o) { return tma_map_tile32(o, base, rows, ld, f32); });
+  }
+  const char* map_halo(CUtensorMap* m, const void* base, int B, int H, int W, int ld) {
+    return cached_map(m, pf_engine::MapKey{base, ((long long)B << 32) | (unsigned)H, W, ld, 3, 0, 0}, [&](CUtensorMap* o) { return tma_map_halo(o, base, B, H, W, ld); });
+  }
   // C[M, N] = A[M, K] W^T : A = split planes with row pitch A.ld, first channel a_c0
   int tgemm(const SplitT& A, long long M, int K, int a_c0, const GemmW& w, int N, const Epi& o) {
     if (dry) return PF_OK;
@@ -370,17 +406,17 @@ struct Fwd {
     TmaMaps maps{};
     const int bn = tma_pick_bn(N, MODE_GEMM), kb = tma_pick_kb(bn, K, MODE_GEMM);
     const char* msg = nullptr;
-    if (!msg) msg = tma_map_2d(&maps.a_hi, A.hi, A.ld, M, A.ld, 128, kb);
-    if (!msg) msg = tma_map_2d(&maps.a_lo, A.lo, A.ld, M, A.ld, 128, kb);
-    if (!msg) msg = tma_map_2d(&maps.b_hi, w.hi, K, N, K, bn, kb);
-    if (!msg) msg = tma_map_2d(&maps.b_lo, w.lo, K, N, K, bn, kb);
+    if (!msg) msg = map2d(&maps.a_hi, A.hi, A.ld, M, A.ld, 128, kb);
+    if (!msg) msg = map2d(&maps.a_lo, A.lo, A.ld, M, A.ld, 128, kb);
+    if (!msg) msg = map2d(&maps.b_hi, w.hi, K, N, K, bn, kb);
+    if (!msg) msg = map2d(&maps.b_lo, w.lo, K, N, K, bn, kb);
     // epilogue tiles go through TMA as well: fp32 output, or (when there is no fp32 output) the split planes; residual
     if (o.C && o.S.hi) return fail(PF_ERR_ARG, "tgemm: fp32 and split outputs together are not supported in GEMM mode");
     if (o.res2 || o.bias_mode == 2) return fail(PF_ERR_ARG, "tgemm: second residual / border-class bias are halo-mode features");
-    if (!msg && o.C) msg = tma_map_tile32(&maps.c, o.C, M, o.ldc, true);
-    if (!msg && o.S.hi) msg = tma_map_tile32(&maps.s_hi, o.S.hi, M, o.S.ld, false);
-    if (!msg && o.S.hi) msg = tma_map_tile32(&maps.s_lo, o.S.lo, M, o.S.ld, false);
-    if (!msg && o.res) msg = tma_map_tile32(&maps.res, o.res, M, o.ldr, true);
+    if (!msg && o.C) msg = map_tile32(&maps.c, o.C, M, o.ldc, true);
+    if (!msg && o.S.hi) msg = map_tile32(&maps.s_hi, o.S.hi, M, o.S.ld, false);
+    if (!msg && o.S.hi) msg = map_tile32(&maps.s_lo, o.S.lo, M, o.S.ld, false);
+    if (!msg && o.res) msg = map_tile32(&maps.res, o.res, M, o.ldr, true);
     if (msg) return fail(PF_ERR_CUDA, "%s", msg);
     maps.a2_hi = maps.a_hi; maps.a2_lo = maps.a_lo;
     if (!o.C) maps.c = maps.a_hi;
@@ -400,15 +436,15 @@ struct Fwd {
     TmaMaps maps{};
     const int bn = tma_pick_bn(N, MODE_HALO), kb = tma_pick_kb(bn, p.K, MODE_HALO);
     const char* msg = nullptr;
-    if (!msg) msg = tma_map_halo(&maps.a_hi, A.hi, B, H, W, A.ld);
-    if (!msg) msg = tma_map_halo(&maps.a_lo, A.lo, B, H, W, A.ld);
+    if (!msg) msg = map_halo(&maps.a_hi, A.hi, B, H, W, A.ld);
+    if (!msg) msg = map_halo(&maps.a_lo, A.lo, B, H, W, A.ld);
     if (A2) {
-      if (!msg) msg = tma_map_halo(&maps.a2_hi, A2->hi, B, H, W, A2->ld);
-      if (!msg) msg = tma_map_halo(&maps.a2_lo, A2->lo, B, H, W, A2->ld);
+      if (!msg) msg = map_halo(&maps.a2_hi, A2->hi, B, H, W, A2->ld);
+      if (!msg) msg = map_halo(&maps.a2_lo, A2->lo, B, H, W, A2->ld);
     } else { maps.a2_hi = maps.a_hi; maps.a2_lo = maps.a_lo; }
     maps.c = maps.a_hi; maps.s_hi = maps.a_hi; maps.s_lo = maps.a_hi; maps.res = maps.a_hi;   // halo mode: epilogue stores from registers
-    if (!msg) msg = tma_map_2d(&maps.b_hi, w.hi, p.K, (long long)groups * N, p.K, bn, kb);
-    if (!msg) msg = tma_map_2d(&maps.b_lo, w.lo, p.K, (long long)groups * N, p.K, bn, kb);
+    if (!msg) msg = map2d(&maps.b_hi, w.hi, p.K, (long long)groups * N, p.K, bn, kb);
+    if (!msg) msg = map2d(&maps.b_lo, w.lo, p.K, (long long)groups * N, p.K, bn, kb);
     if (msg) return fail(PF_ERR_CUDA, "%s", msg);
     return launch_tma(MODE_HALO, maps, p);
   }
