@@ -241,11 +241,29 @@ def main():
     d2h_bytes = sum(v.numel() * 4 for v in host.values())
     h2d_bytes = sum(im.size for im in imgs)
 
-    def e2e_step():
+    # device->host reads of step k run on a side stream (after an event on the compute stream) so that they overlap the
+    # forward of step k+1; two sets of pinned buffers; both streams are drained before the end-of-region timestamp.
+    copy_stream = torch.cuda.Stream(device=dev)
+    host2 = {k: torch.empty_like(v).pin_memory() for k, v in host.items()}
+    pending = []
+
+    def e2e_step(it=[0]):
         r = model.inference_batch(imgs)
-        for i, d in enumerate(r):
-            for k in keys:
-                host[k][i].copy_(d[k], non_blocking=True)
+        done = torch.cuda.Event()
+        done.record()
+        bufs = host if it[0] % 2 == 0 else host2
+        it[0] += 1
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(done)
+            for i, d in enumerate(r):
+                for k in keys:
+                    bufs[k][i].copy_(d[k], non_blocking=True)
+                    d[k].record_stream(copy_stream)
+        if len(pending) >= 2:
+            pending.pop(0).synchronize()    # the buffers about to be reused have been filled
+        ev = torch.cuda.Event()
+        ev.record(copy_stream)
+        pending.append(ev)
 
     for _ in range(max(args.warmup, 1)):
         e2e_step()
@@ -255,6 +273,7 @@ def main():
     f0.record()
     for _ in range(args.steps):
         e2e_step()
+    torch.cuda.current_stream(dev).wait_stream(copy_stream)   # the last read-back is inside the timed region
     f1.record()
     barrier()
     wall_ms = (time.perf_counter() - tw) * 1000
@@ -272,6 +291,13 @@ def main():
         pass
     peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16, kernel timed inside a long step)" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+    traffic, traffic_src = None, None
+    try:   # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/)
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_dominant_kernel.json")) as f:
+            t = json.load(f)
+        traffic, traffic_src = t["dram_bytes_per_launch"], t["source"]
+    except Exception:
+        pass
     cfg_names = ["conv_gemm_kernel<128,128> (HMMA)", "conv_gemm_kernel<128,64> (HMMA)", "conv_gemm_kernel<128,32> (HMMA)",
                  "conv_gemm_tc_kernel<BN> (tcgen05.mma kind::f16 + TMEM, bf16x3 split-precision implicit GEMM, 128 x BN tiles)",
                  "conv3x3_tc_kernel<BN> (tcgen05.mma kind::f16 + TMEM, bf16x3 split precision, halo-tile 3x3 convolution, 16x8-pixel x BN tiles)",
@@ -286,7 +312,7 @@ def main():
     roofline = {
         "bound": "tensor", "kernel": cfg_names[dom],
         "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None,
-        "traffic": None, "peak_source": peak_src,
+        "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
         "note": "achieved = algorithmic 2*M*N*K FLOPs / CUDA-event time of this kernel's launches, measured live in a second pass of the same K steps "
                 "(event pairs on the launch stream around every GEMM launch; kept out of the `value` region); every product costs "
                 "3 bf16 MMAs (lo*hi + hi*lo + hi*hi) to meet the 1e-3 fp32 tolerance, so the ceiling of this scheme is peak/3 (frac 0.33)",
