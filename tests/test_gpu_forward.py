@@ -198,3 +198,25 @@ def test_legacy_engines_end_to_end(opts):
     compare_with_golden(version, out, tol=TOL)
     for a, b in zip(out, base):
         assert U.rel_err(a["pred_latitude"], b["pred_latitude"]) < 1e-4
+
+
+def test_resolution_sweep_large_image_properties_and_parity():
+    """BASELINE config C5 shape class: 2048x1536 and 1024x768 inputs (only the pre/post-processing bytes change)."""
+    version = "PersNet_Paramnet-GSV-uncentered"
+    m, sd = model(version)
+    imgs = [wg.smooth_images(1, 1536, 2048, 21)[0], wg.synth_images(1, 768, 1024, 22)[0]]
+    out = m.inference_batch(imgs)
+    _check(out, om.inference_batch(sd, version, imgs), version)
+    assert out[0]["pred_gravity_original"].shape == (2, 1536, 2048) and out[1]["pred_latitude_original"].shape == (768, 1024)
+    assert (out[0]["pred_gravity_original"].norm(dim=0) - 1).abs().max() < 1e-5
+
+
+def test_c3_shape_512x512_batch():
+    """BASELINE config C3 shape: 512x512 inputs, uncentered ParamNet (64x64 nearest sub-sample), batch 8 here."""
+    version = "Paramnet-360Cities-edina-uncentered"
+    m, sd = model(version)
+    imgs = wg.synth_images(8, 512, 512, 31)
+    out = m.inference_batch(imgs)
+    _check([out[3]], om.inference_batch(sd, version, [imgs[3]]), version)
+    for o in out:
+        assert torch.isfinite(o["pred_rel_focal"]) and o["pred_rel_focal"] > 0
