@@ -3,9 +3,9 @@
 // q k^T and p v, fp32 softmax.  Replaces the CUDA-core attention_kernel (layers.cuh) on the forward path; ~12 % of the
 // step there.
 //
-//   block = 4 warps, one (image, head); K and V of the head are split once into bf16 hi/lo planes in shared memory
+//   block = 4 warps (3 blocks per SM), one (image, head); K and V of the head are split once into bf16 hi/lo planes in shared memory
 //   (keys padded 100 -> 112, rows of 128 B, 16 B chunks XOR-swizzled for conflict-free ldmatrix); the block then loops over
-//   tiles of 64 queries (16 per warp).  Per warp and tile: S = q k^T (mma.sync.m16n8k16, 4 k-steps x 14 key tiles x 3),
+//   passes of 64 queries (16 per warp); passes per block are chosen so that the grid is about one resident wave.  Per warp and tile: S = q k^T (mma.sync.m16n8k16, 4 k-steps x 14 key tiles x 3),
 //   row softmax in registers (quad shuffles), O = P V (7 k-steps x 8 tiles x 3; P re-used from the S accumulators as the A
 //   operand, V through ldmatrix.trans), normalise, store fp32 and/or split planes.
 #pragma once
@@ -13,7 +13,7 @@
 
 namespace pf {
 
-constexpr int kAmKeys = 100, kAmKeysPad = 112, kAmD = 64, kAmQTile = 64, kAmThreads = 128;
+constexpr int kAmKeys = 100, kAmKeysPad = 112, kAmD = 64, kAmQTile = 64, kAmThreads = 128;   // 4 warps x 16 queries per pass
 constexpr int kAmPlane = kAmKeysPad * kAmD * 2;      // bytes of one bf16 plane (K or V, hi or lo)
 constexpr int kAmSmem = 4 * kAmPlane;                // K_hi, K_lo, V_hi, V_lo = 57344 B
 
@@ -171,7 +171,10 @@ inline cudaError_t attention_mma_launch(const float* q, const float* kv, float* 
     configured = true;
   }
   const int tiles = cdiv(N, kAmQTile);
-  const int tpb = tiles >= 16 ? 4 : (tiles >= 4 ? 2 : 1);   // amortise the K/V staging over several query tiles
+  // passes per block: the grid should be about one resident wave (148 SMs x 3 blocks); the K/V staging of a block is
+  // amortised over tpb * 64 queries
+  int tpb = (tiles * heads * B) / 400;
+  tpb = tpb < 1 ? 1 : (tpb > tiles ? tiles : tpb);
   dim3 grid(cdiv(tiles, tpb), heads, B);
   attention_mma_kernel<<<grid, kAmThreads, kAmSmem, st>>>(q, kv, out, sp.hi, sp.lo, N, C, tpb);
   return cudaGetLastError();

@@ -78,36 +78,42 @@ inline cudaError_t stem_conv_launch(const float* in, int ldin, int B, int H, int
 // LayerNorm over the channel dimension of [rows, C] (nn.LayerNorm / F.layer_norm, biased variance, eps inside
 // the sqrt) -- mix_transformers.py:199-200,247,120,457 and convnext.py:172-182 (both data formats reduce to this
 // in NHWC).  One warp per row; two-pass (mean, then centred variance) in registers.
-template <int MAXQ>   // float4 quads per lane: lane owns channels [4*(lane + 32*i), +4)
+template <int MAXQ, int LANES>   // float4 quads per lane; LANES (32 or 16) lanes cooperate on one row: lane owns quads lane + LANES*i
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ in, float* __restrict__ out, long long rows, int C,
                                                         const float* __restrict__ gw, const float* __restrict__ gb, float eps,
                                                         __nv_bfloat16* __restrict__ shi, __nv_bfloat16* __restrict__ slo) {
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const int lane = threadIdx.x & 31;
+  constexpr int RPW = 32 / LANES;       // rows per warp
+  const int lane = threadIdx.x & (LANES - 1);
+  const long long row = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + ((threadIdx.x & 31) / LANES);
+  const bool ok = row < rows;
   const int Q = C >> 2;
-  const float4* x = reinterpret_cast<const float4*>(in + row * C);
+  const float4* x = reinterpret_cast<const float4*>(in + (ok ? row : 0) * C);
   float4 v[MAXQ];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < MAXQ; ++i) {
-    const int qd = lane + 32 * i;
-    v[i] = qd < Q ? x[qd] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int qd = lane + LANES * i;
+    v[i] = (ok && qd < Q) ? x[qd] : make_float4(0.f, 0.f, 0.f, 0.f);
     s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   }
-  const float mean = warp_sum(s) / (float)C;
+#pragma unroll
+  for (int o = LANES / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)C;
   float q = 0.f;
 #pragma unroll
   for (int i = 0; i < MAXQ; ++i) {
-    if (lane + 32 * i < Q) {
+    if (lane + LANES * i < Q) {
       const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
       q = fmaf(a, a, q); q = fmaf(b, b, q); q = fmaf(c, c, q); q = fmaf(d, d, q);
     }
   }
-  const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
+#pragma unroll
+  for (int o = LANES / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = 1.0f / sqrtf(q / (float)C + eps);
+  if (!ok) return;
 #pragma unroll
   for (int i = 0; i < MAXQ; ++i) {
-    const int qd = lane + 32 * i;
+    const int qd = lane + LANES * i;
     if (qd < Q) {
       const float4 w = __ldg(reinterpret_cast<const float4*>(gw) + qd), b = __ldg(reinterpret_cast<const float4*>(gb) + qd);
       const float4 y = make_float4((v[i].x - mean) * rstd * w.x + b.x, (v[i].y - mean) * rstd * w.y + b.y,
@@ -121,10 +127,10 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 inline cudaError_t layernorm_launch(const float* in, float* out, long long rows, int C, const float* w, const float* b, float eps,
                                     cudaStream_t st, SplitT sp = SplitT()) {
   if (C % 4 || C > 768) return cudaErrorInvalidValue;
-  const unsigned grid = (unsigned)cdivl(rows, 8);
-  if (C <= 128) layernorm_kernel<1><<<grid, 256, 0, st>>>(in, out, rows, C, w, b, eps, sp.hi, sp.lo);
-  else if (C <= 384) layernorm_kernel<3><<<grid, 256, 0, st>>>(in, out, rows, C, w, b, eps, sp.hi, sp.lo);
-  else layernorm_kernel<6><<<grid, 256, 0, st>>>(in, out, rows, C, w, b, eps, sp.hi, sp.lo);
+  if (C <= 64) layernorm_kernel<1, 16><<<(unsigned)cdivl(rows, 16), 256, 0, st>>>(in, out, rows, C, w, b, eps, sp.hi, sp.lo);   // two rows per warp
+  else if (C <= 128) layernorm_kernel<1, 32><<<(unsigned)cdivl(rows, 8), 256, 0, st>>>(in, out, rows, C, w, b, eps, sp.hi, sp.lo);
+  else if (C <= 384) layernorm_kernel<3, 32><<<(unsigned)cdivl(rows, 8), 256, 0, st>>>(in, out, rows, C, w, b, eps, sp.hi, sp.lo);
+  else layernorm_kernel<6, 32><<<(unsigned)cdivl(rows, 8), 256, 0, st>>>(in, out, rows, C, w, b, eps, sp.hi, sp.lo);
   return cudaGetLastError();
 }
 
@@ -223,12 +229,12 @@ __global__ void __launch_bounds__(256) dwconv3x3_gelu_kernel(const float* __rest
                                                              __nv_bfloat16* __restrict__ shi = nullptr, __nv_bfloat16* __restrict__ slo = nullptr) {
   // thread = 4 channels x 4 consecutive pixels of one row: 18 activation + 9 weight loads for 4 outputs
   const int C4 = C >> 2, XG = (W + 3) >> 2;
-  const long long total = (long long)B * H * XG * C4;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c4 = (int)(i % C4);
-    long long r = i / C4;
-    const int xg = (int)(r % XG); r /= XG;
-    const int y = (int)(r % H); const int b = (int)(r / H);
+  const unsigned total = (unsigned)B * H * XG * C4;      // < 2^31 for every layer of the network: 32-bit index math
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % (unsigned)C4);
+    unsigned r = i / (unsigned)C4;
+    const int xg = (int)(r % (unsigned)XG); r /= (unsigned)XG;
+    const int y = (int)(r % (unsigned)H); const int b = (int)(r / (unsigned)H);
     const int x0 = xg * 4;
     const float4 bv = __ldg(reinterpret_cast<const float4*>(bias) + c4);
     float4 acc[4] = {bv, bv, bv, bv};
@@ -268,12 +274,12 @@ __global__ void __launch_bounds__(256) dwconv3x3_gelu_kernel(const float* __rest
 __global__ void __launch_bounds__(256) dwconv7x7_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C,
                                                         const float* __restrict__ w, const float* __restrict__ bias) {
   const int C4 = C >> 2, XG = (W + 3) >> 2;
-  const long long total = (long long)B * H * XG * C4;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c4 = (int)(i % C4);
-    long long r = i / C4;
-    const int xg = (int)(r % XG); r /= XG;
-    const int y = (int)(r % H); const int b = (int)(r / H);
+  const unsigned total = (unsigned)B * H * XG * C4;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % (unsigned)C4);
+    unsigned r = i / (unsigned)C4;
+    const int xg = (int)(r % (unsigned)XG); r /= (unsigned)XG;
+    const int y = (int)(r % (unsigned)H); const int b = (int)(r / (unsigned)H);
     const int x0 = xg * 4;
     const float4 bv = __ldg(reinterpret_cast<const float4*>(bias) + c4);
     float4 acc[4] = {bv, bv, bv, bv};
@@ -318,12 +324,12 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const float* __restrict
                                                          int B, int H, int W, int C, __nv_bfloat16* __restrict__ shi = nullptr, __nv_bfloat16* __restrict__ slo = nullptr) {
   // thread = 8 channels of one output pixel (16 B stores to each bf16 plane)
   const int C8 = C >> 3, OH = 2 * H, OW = 2 * W;
-  const long long total = (long long)B * OH * OW * C8;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % C8);
-    long long pix = i / C8;
-    const int x = (int)(pix % OW); pix /= OW;
-    const int y = (int)(pix % OH); const int b = (int)(pix / OH);
+  const unsigned total = (unsigned)B * OH * OW * C8;     // <= 2^29 for the network's largest tensor at batch 32
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % (unsigned)C8);
+    unsigned pix = i / (unsigned)C8;
+    const int x = (int)(pix % (unsigned)OW); pix /= (unsigned)OW;
+    const int y = (int)(pix % (unsigned)OH); const int b = (int)(pix / (unsigned)OH);
     const float sy = fmaxf(0.5f * (y + 0.5f) - 0.5f, 0.f), sx = fmaxf(0.5f * (x + 0.5f) - 0.5f, 0.f);
     const int y0 = (int)sy, x0 = (int)sx;
     const int y1 = y0 + (y0 < H - 1), x1 = x0 + (x0 < W - 1);
@@ -379,6 +385,39 @@ __global__ void __launch_bounds__(256) im2col_split_kernel(const __nv_bfloat16* 
       h = __ldg(reinterpret_cast<const uint4*>(shi + si));
       l = __ldg(reinterpret_cast<const uint4*>(slo + si));
     }
+    reinterpret_cast<uint4*>(dhi)[i] = h;
+    reinterpret_cast<uint4*>(dlo)[i] = l;
+  }
+}
+
+// Patch gather for the 7x7 stems (patch_embed1: stride 4, ll_enc: stride 2; pad 3) straight from the normalised input
+// x0 [B,320,320,4] fp32 (b,g,r,0): dst[m][(ky*7+kx)*3 + c] split into bf16 hi/lo, K padded 147 -> 160 with zeros, so that the
+// stems run on the TMA GEMM engine too.  One thread = one output pixel x 8 consecutive K columns (16 B per plane).
+__global__ void __launch_bounds__(256) stem_gather_kernel(const float* __restrict__ x0, __nv_bfloat16* __restrict__ dhi, __nv_bfloat16* __restrict__ dlo,
+                                                          int B, int OH, int OW, int stride) {
+  constexpr int KP = 160, KQ = KP / 8;
+  const unsigned total = (unsigned)B * OH * OW * KQ;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int kq = (int)(i % KQ);
+    unsigned m = i / KQ;
+    const int ox = (int)(m % (unsigned)OW); unsigned t = m / (unsigned)OW;
+    const int oy = (int)(t % (unsigned)OH); const int b = (int)(t / (unsigned)OH);
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = kq * 8 + e;
+      float val = 0.f;
+      if (k < 147) {
+        const int tap = k / 3, c = k - tap * 3;
+        const int ky = tap / 7, kx = tap - ky * 7;
+        const int iy = oy * stride - 3 + ky, ix = ox * stride - 3 + kx;
+        if ((unsigned)iy < (unsigned)kNet && (unsigned)ix < (unsigned)kNet) val = __ldg(x0 + ((long long)(b * kNet + iy) * kNet + ix) * 4 + c);
+      }
+      v[e] = val;
+    }
+    uint4 h, l;
+    split_bf16x2(v[0], v[1], h.x, l.x); split_bf16x2(v[2], v[3], h.y, l.y);
+    split_bf16x2(v[4], v[5], h.z, l.z); split_bf16x2(v[6], v[7], h.w, l.w);
     reinterpret_cast<uint4*>(dhi)[i] = h;
     reinterpret_cast<uint4*>(dlo)[i] = l;
   }

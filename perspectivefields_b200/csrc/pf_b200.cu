@@ -98,6 +98,7 @@ struct pf_engine {
   const float *embed1_w, *embed1_b, *llenc_w, *llenc_b;
   LnW embed_ln[4], stage_norm[4];
   GemmW embed[4];  // [1..3] used
+  GemmW embed1g, llencg;  // 7x7 stems as [64][160] GEMMs (tensor-core path)
   std::vector<MitBlockW> blocks[4];
   GemmW proc[4];   // composed linear_c{l} o linear_c{l}_proc, both heads side by side (N = 512), index lvl-1
   GemmW rcu[4][2][2];  // [fusion-1][unit-1][conv-1], grouped over the two heads
@@ -126,6 +127,7 @@ struct pf_engine {
     }
   };
   std::unordered_map<MapKey, CUtensorMap, MapKeyHash> map_cache;
+  bool use_stem_tc = true;    // 7x7 stems as patch gather + TMA GEMM (option "stem_tc"; 0 = fp32 CUDA-core direct convolution)
   bool use_attn_mma = true;   // tensor-core attention core (option "attn_mma"; 0 = CUDA-core fp32 kernel)
   bool use_tma = true;   // whole forward on the TMA -> tcgen05 engine with pre-split activations (option "tma"; 0 = legacy engines)
   int sm_count = 148;
@@ -168,6 +170,8 @@ static int resolve_weights(pf_engine* e) {
   TRY(get_f(e, "embed1.b", 64, &e->embed1_b));
   TRY(get_f(e, "llenc.w", 147 * 64, &e->llenc_w));
   TRY(get_f(e, "llenc.b", 64, &e->llenc_b));
+  TRY(get_gemm(e, "embed1g", 64, 160, 64, &e->embed1g));
+  TRY(get_gemm(e, "llencg", 64, 160, 64, &e->llencg));
   for (int s = 0; s < 4; ++s) {
     const int C = kMitDims[s];
     snprintf(nm, sizeof nm, "embed%d.ln", s + 1);
@@ -797,7 +801,17 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
   SplitT cfeat[4];
   for (int s = 0; s < 4; ++s) cfeat[s] = F.salloc((long long)n * kMitRes[s] * kMitRes[s], kMitDims[s]);
   SplitT ll = F.salloc((long long)n * 160 * 160, 64);
-  if (!dry) LAUNCHED((stem_conv_launch<7, 7, 2, 3, 64>(x0, 4, n, kNet, kNet, e->llenc_w, e->llenc_b, nullptr, 1, st, ll)));
+  if (e->use_stem_tc) {   // conv7x7/2 (+ folded BN + ReLU) as patch gather + TMA GEMM (K = 147 padded to 160)
+    const long long m = ar.mark();
+    const long long M = (long long)n * 160 * 160;
+    SplitT col = F.salloc(M, 160);
+    if (!dry) LAUNCHED((stem_gather_kernel<<<ew_grid(M * 20), 256, 0, st>>>(x0, col.hi, col.lo, n, 160, 160, 2), cudaGetLastError()));
+    Epi o; o.S = ll; o.act = 1;
+    TRY(F.tgemm(col, M, 160, 0, e->llencg, 64, o));
+    ar.release(m);
+  } else if (!dry) {
+    LAUNCHED((stem_conv_launch<7, 7, 2, 3, 64>(x0, 4, n, kNet, kNet, e->llenc_w, e->llenc_b, nullptr, 1, st, ll)));
+  }
   TRY(F.tap_split("ll", ll, (long long)n * 160 * 160 * 64));
 
   // ---------------- MiT-B3 encoder ---------------------------------------------------------------------------
@@ -815,7 +829,14 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
     float* kv = ar.f((long long)n * 100 * 2 * C);
     float* h1 = ar.f(rows * 4 * C);
     SplitT h2 = F.salloc(rows, 4 * C);
-    if (s == 0) {
+    if (s == 0 && e->use_stem_tc) {
+      const long long mm = ar.mark();
+      SplitT col = F.salloc(rows, 160);
+      if (!dry) LAUNCHED((stem_gather_kernel<<<ew_grid(rows * 20), 256, 0, st>>>(x0, col.hi, col.lo, n, 80, 80, 4), cudaGetLastError()));
+      Epi o; o.C = tf; o.ldc = C;
+      TRY(F.tgemm(col, rows, 160, 0, e->embed1g, 64, o));
+      ar.release(mm);
+    } else if (s == 0) {
       if (!dry) LAUNCHED((stem_conv_launch<7, 7, 4, 3, 64>(x0, 4, n, kNet, kNet, e->embed1_w, e->embed1_b, tf, 0, st)));
     } else {
       Epi o; o.C = tf; o.ldc = C;
@@ -1060,6 +1081,7 @@ int pf_set_option(pf_handle h, const char* name, int value) {
   if (!strcmp(name, "halo3x3")) { h->use_halo = value != 0; return PF_OK; }
   if (!strcmp(name, "tma")) { h->use_tma = value != 0; return PF_OK; }
   if (!strcmp(name, "attn_mma")) { h->use_attn_mma = value != 0; return PF_OK; }
+  if (!strcmp(name, "stem_tc")) { h->use_stem_tc = value != 0; return PF_OK; }
   return fail(PF_ERR_ARG, "pf_set_option: unknown option '%s'", name);
 }
 // out[cfg*3 + {0,1,2}] = {milliseconds, algorithmic FLOPs, launches} per GEMM engine configuration (7 configs),

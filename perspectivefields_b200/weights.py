@@ -74,6 +74,12 @@ def repack(sd, cfg):
     scale = sd["ll_enc.bn1.weight"].double() / torch.sqrt(sd["ll_enc.bn1.running_var"].double() + 1e-5)
     out["llenc.w"] = _stem((sd["ll_enc.conv1.weight"].double() * scale[:, None, None, None]).float())
     out["llenc.b"] = (sd["ll_enc.bn1.bias"].double() - sd["ll_enc.bn1.running_mean"].double() * scale).float().contiguous()
+    # the same two 7x7 stems as [64][160] GEMM weights (K = (ky,kx,c) padded 147 -> 160 with zeros) for the tensor-core path
+    for name, w, b in (("embed1g", sd[bb + "patch_embed1.proj.weight"].double(), out["embed1.b"]),
+                       ("llencg", sd["ll_enc.conv1.weight"].double() * scale[:, None, None, None], out["llenc.b"])):
+        wk = torch.zeros(64, 160, dtype=torch.float64)
+        wk[:, :147] = w.permute(0, 2, 3, 1).reshape(64, 147)
+        _put_gemm(out, name, wk, b)
     # ---- MiT-B3
     for s, C in enumerate(MIT_DIMS):
         _put_ln(out, f"embed{s + 1}.ln", sd, f"{bb}patch_embed{s + 1}.norm")
