@@ -47,7 +47,8 @@ def parse():
 
 class ClockSampler:
     """SM clock / throttle-reason samples DURING the timed region (B200_PROFILING.md recipe), read through NVML from the
-    main thread right after each step has been enqueued (the GPU is then busy with that step and the host is far ahead of it).
+    main thread once all K steps have been enqueued, repeatedly until the end event completes (the GPU is busy with the queued
+    steps; sampling between the enqueues starved the GPU on boxes where one NVML call takes ~40 ms).
     A concurrent poller -- an `nvidia-smi -lms` child or an NVML thread -- measurably slowed the launches it was observing."""
 
     def __init__(self, index):
@@ -206,9 +207,13 @@ def main():
         h0 = time.perf_counter()
         out = eng.forward(B, heights, widths, blob=blob, offsets=offsets)
         host_fwd += time.perf_counter() - h0
-        sampler.sample()   # this step is now executing (or queued) on the GPU
     e1.record()
     host_enqueue_ms = (time.perf_counter() - host_t0) * 1000 / args.steps
+    # clock samples DURING the timed region: the host is ahead of the GPU here (all K steps are queued), so the NVML calls
+    # (tens of ms each on some boxes) overlap the GPU work instead of delaying launches
+    sampler.sample()
+    while not e1.query() and len(sampler.rows) < 64:
+        sampler.sample()
     barrier()
     ms = e0.elapsed_time(e1)
     launches = L.pf_kernel_launch_count() - launches0

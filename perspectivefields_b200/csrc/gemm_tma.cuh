@@ -45,6 +45,10 @@ struct TmaGemmParams {
   const float* res2; int ldr2, r2_coff, r2_gcoff;
   float* C; int ldc, c_coff, c_gcoff;                                           // fp32 output (may be null)
   __nv_bfloat16* Shi; __nv_bfloat16* Slo; int lds, s_coff, s_gcoff, split_relu; // split output (may be null)
+  // MODE_HALO, N = 32 (conv_fuse_conv1): fused prediction tail -- 1x1 conv 32 -> pred_nc (gravity_head.py:175 /
+  // latitude_head.py:174) + F.normalize (pred_mode 1, gravity_head.py:192-193) or clamp to [-1,1] (pred_mode 2,
+  // latitude_head.py:191-192), written NCHW to pred_out; replaces the separate pred_tail_kernel pass over conv1's output
+  const float* pred_w; const float* pred_b; float* pred_out; int pred_nc, pred_mode;
 };
 
 // KB = K elements per pipeline step: 32 (64 B rows, SWIZZLE_64B) for wide tiles, 64 (128 B rows, SWIZZLE_128B) for BN <= 128
@@ -459,6 +463,27 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
             for (int j = 0; j < 32; j += 4) {
               const float4 rv = *reinterpret_cast<const float4*>(rp + j);
               o[j] += rv.x; o[j + 1] += rv.y; o[j + 2] += rv.z; o[j + 3] += rv.w;
+            }
+          }
+          if (MODE == MODE_HALO && BN == 32 && p.pred_w) {
+            float v0 = __ldg(p.pred_b), v1 = p.pred_nc > 1 ? __ldg(p.pred_b + 1) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.pred_w + j));
+              v0 = fmaf(o[j], w0.x, v0); v0 = fmaf(o[j + 1], w0.y, v0); v0 = fmaf(o[j + 2], w0.z, v0); v0 = fmaf(o[j + 3], w0.w, v0);
+              if (p.pred_nc > 1) {
+                const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.pred_w + 32 + j));
+                v1 = fmaf(o[j], w1.x, v1); v1 = fmaf(o[j + 1], w1.y, v1); v1 = fmaf(o[j + 2], w1.z, v1); v1 = fmaf(o[j + 3], w1.w, v1);
+              }
+            }
+            const long long HWl = (long long)p.H * p.W;
+            const long long bi = m / HWl, pix = m - bi * HWl;
+            float* po = p.pred_out + bi * p.pred_nc * HWl + pix;
+            if (p.pred_mode == 1) {
+              const float nrm = fmaxf(sqrtf(v0 * v0 + v1 * v1), 1e-12f);
+              po[0] = v0 / nrm; po[HWl] = v1 / nrm;
+            } else {
+              po[0] = fminf(fmaxf(v0, -1.f), 1.f);
             }
           }
           if (p.C) {

@@ -45,11 +45,20 @@ static int fail(int code, const char* fmt, ...) {
     cudaError_t e__ = (expr);                                                                       \
     if (e__ != cudaSuccess) return fail(PF_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
   } while (0)
+// PF_SYNC_DEBUG=1 in the environment: synchronise after every launch so that a device fault is reported at the launch that
+// caused it (debugging aid; never set in production)
+static char g_crumb[96] = "";   // name of the last debug tap taken (breadcrumb for the error text)
+static bool sync_debug() {
+  static int v = -1;
+  if (v < 0) v = getenv("PF_SYNC_DEBUG") ? 1 : 0;
+  return v == 1;
+}
 #define LAUNCHED(expr)                                                                              \
   do {                                                                                              \
     cudaError_t e__ = (expr);                                                                       \
     g_launches.fetch_add(1, std::memory_order_relaxed);                                             \
-    if (e__ != cudaSuccess) return fail(PF_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    if (e__ == cudaSuccess && sync_debug()) e__ = cudaDeviceSynchronize();                          \
+    if (e__ != cudaSuccess) return fail(PF_ERR_CUDA, "%s: %s (%s:%d, after tap '%s')", #expr, cudaGetErrorString(e__), __FILE__, __LINE__, g_crumb); \
   } while (0)
 #define TRY(expr)                \
   do {                           \
@@ -267,7 +276,10 @@ struct Fwd {
     if (!e->debug) return PF_OK;
     float* cp = ar.f(numel);
     if (dry) return PF_OK;
+    snprintf(g_crumb, sizeof g_crumb, "%s", name);
+    if (sync_debug()) fprintf(stderr, "[pf tap] %s cp=%p (+%lld of cap %lld) p=%p numel=%lld\n", name, (void*)cp, (long long)((char*)cp - ar.base), ar.cap, (const void*)p, numel);
     CU(cudaMemcpyAsync(cp, p, numel * 4, cudaMemcpyDeviceToDevice, st));
+    if (sync_debug()) CU(cudaDeviceSynchronize());
     e->taps.push_back({name, {cp, numel}});
     return PF_OK;
   }
@@ -338,11 +350,12 @@ struct Fwd {
     if (!e->debug) return PF_OK;
     float* cp = ar.f(numel);
     if (dry) return PF_OK;
+    snprintf(g_crumb, sizeof g_crumb, "%s", name);
     LAUNCHED((merge_split_kernel<<<(unsigned)cdivl(numel, 256), 256, 0, st>>>(t.hi, t.lo, cp, numel), cudaGetLastError()));
     e->taps.push_back({name, {cp, numel}});
     return PF_OK;
   }
-  int launch_tma(int mode, const TmaMaps& maps, const TmaGemmParams& p) {
+  int launch_tma(int mode, const TmaMaps& maps, const TmaGemmParams& p, const PredTail* pred = nullptr) {
     const int bn = tma_pick_bn(p.N, mode), kb = tma_pick_kb(bn, p.K, mode);
     if (e->profile) {
       pf_engine::ProfRec r{};
@@ -355,12 +368,12 @@ struct Fwd {
       r.cfg = mode == MODE_GEMM ? 5 : 6;
       r.M = (int)Mrows; r.N = p.N; r.K = p.K; r.KH = mode == MODE_GEMM ? 1 : 3; r.stride = 1; r.groups = p.groups; r.Cin = p.Cin;
       CU(cudaEventRecord(r.a, st));
-      LAUNCHED(gemm_tma_launch(mode, maps, p, bn, kb, e->sm_count, st));
+      LAUNCHED(gemm_tma_launch(mode, maps, p, bn, kb, e->sm_count, st, pred));
       CU(cudaEventRecord(r.b, st));
       e->prof.push_back(r);
       return PF_OK;
     }
-    LAUNCHED(gemm_tma_launch(mode, maps, p, bn, kb, e->sm_count, st));
+    LAUNCHED(gemm_tma_launch(mode, maps, p, bn, kb, e->sm_count, st, pred));
     return PF_OK;
   }
   struct Epi {   // epilogue options of one TMA GEMM / conv
@@ -430,7 +443,7 @@ struct Fwd {
   }
   // 3x3 / stride 1 / pad 1 convolution on split NHWC planes (optionally a second source for channels >= c_split)
   int thalo(const SplitT& A, int a_c0, int a_gc, const SplitT* A2, int c_split, int a2_c0, int B, int H, int W, int Cin, const GemmW& w, int N,
-            int groups, int bias_gstride, const Epi& o) {
+            int groups, int bias_gstride, const Epi& o, const PredTail* pred = nullptr) {
     if (dry) return PF_OK;
     if (Cin % 64 || N % 32 || (A2 && c_split % 64)) return fail(PF_ERR_ARG, "thalo: Cin must be a multiple of 64, N of 32");
     TmaGemmParams p{};
@@ -450,7 +463,7 @@ struct Fwd {
     if (!msg) msg = map2d(&maps.b_hi, w.hi, p.K, (long long)groups * N, p.K, bn, kb);
     if (!msg) msg = map2d(&maps.b_lo, w.lo, p.K, (long long)groups * N, p.K, bn, kb);
     if (msg) return fail(PF_ERR_CUDA, "%s", msg);
-    return launch_tma(MODE_HALO, maps, p);
+    return launch_tma(MODE_HALO, maps, p, pred);
   }
   // strided / patchifying convolution = patch gather on split planes + TMA GEMM
   int tconv_gather(const SplitT& A, int B, int H, int W, int Cin, int KH, int stride, int pad, const GemmW& w, int N, const Epi& o) {
@@ -554,7 +567,7 @@ static int fwd_preprocess(Fwd& F, const pf_batch* bt, float*& x0, PreImage*& d_p
 
 // prediction 1x1 convs (+ normalise / clamp) -> NCHW outputs, then argmax decode (classification) and resample to the
 // original resolutions.  conv1_out: [n,320,320,64] fp32 (gravity head channels 0-31, latitude head 32-63).
-static int fwd_tails_post(Fwd& F, const pf_batch* bt, const float* conv1_out, PostImage* d_post) {
+static int fwd_tails_post(Fwd& F, const pf_batch* bt, const float* conv1_out, PostImage* d_post, bool pred_done = false) {
   pf_engine* e = F.e;
   const pf_model_desc& D = e->desc;
   const int n = F.n;
@@ -563,7 +576,7 @@ static int fwd_tails_post(Fwd& F, const pf_batch* bt, const float* conv1_out, Po
   Arena& ar = F.ar;
   // prediction tails -> NCHW outputs (returned to the caller)
   const int HW = kNet * kNet;
-  if (!dry) {
+  if (!dry && !pred_done) {
     const unsigned grid = (unsigned)cdivl((long long)n * HW, 128);
     LAUNCHED((pred_tail_kernel<<<grid, 128, D.gravity_classes * 33 * 4, st>>>(conv1_out, 64, 0, e->pred_g_w, e->pred_g_b, bt->pred_gravity, n, HW,
                                                                            D.gravity_classes, D.gravity_classes == 2 ? 1 : 0), cudaGetLastError()));
@@ -587,14 +600,16 @@ static int fwd_tails_post(Fwd& F, const pf_batch* bt, const float* conv1_out, Po
   }
   if (!dry) {
     std::vector<PostImage> post(n);
-    long long total = 0;
+    long long total = 0, max_quads = 1;
     for (int i = 0; i < n; ++i) {
       post[i] = PostImage{bt->height[i], bt->width[i], bt->gravity_original_offset[i], bt->latitude_original_offset[i], total};
       total += (long long)bt->height[i] * bt->width[i];
+      const long long quads = (long long)bt->height[i] * ((bt->width[i] + 3) / 4);
+      if (quads > max_quads) max_quads = quads;
     }
     CU(cudaMemcpyAsync(d_post, post.data(), n * sizeof(PostImage), cudaMemcpyHostToDevice, st));
-    LAUNCHED((postprocess_kernel<<<(unsigned)cdivl(total, 256), 256, 0, st>>>(vec, lat, d_post, n, total, bt->gravity_original, bt->latitude_original,
-                                                                             cls_l ? 0 : 1), cudaGetLastError()));
+    LAUNCHED((postprocess_kernel<<<dim3((unsigned)cdivl(max_quads, 256), (unsigned)n), 256, 0, st>>>(vec, lat, d_post, n, total, bt->gravity_original,
+                                                                                                     bt->latitude_original, cls_l ? 0 : 1), cudaGetLastError()));
   }
 
   return PF_OK;
@@ -610,14 +625,14 @@ static int run_forward(Fwd& F, const pf_batch* bt, int max_h_for_dry) {
 
   float* x0; PreImage* d_pre; PostImage* d_post;
   TRY(fwd_preprocess(F, bt, x0, d_pre, d_post));
-  F.tap("pre", x0, (long long)n * kNet * kNet * 4);
+  TRY(F.tap("pre", x0, (long long)n * kNet * kNet * 4));
 
   // ---------------- persistent feature maps ---------------------------------------------------------------
   float* cfeat[4];
   for (int s = 0; s < 4; ++s) cfeat[s] = ar.f((long long)n * kMitRes[s] * kMitRes[s] * kMitDims[s]);
   float* ll = ar.f((long long)n * 160 * 160 * 64);
   if (!dry) LAUNCHED((stem_conv_launch<7, 7, 2, 3, 64>(x0, 4, n, kNet, kNet, e->llenc_w, e->llenc_b, ll, 1, st)));
-  F.tap("ll", ll, (long long)n * 160 * 160 * 64);
+  TRY(F.tap("ll", ll, (long long)n * 160 * 160 * 64));
 
   // ---------------- MiT-B3 encoder (mix_transformers.py:449-485) -------------------------------------------
   for (int s = 0; s < 4; ++s) {
@@ -640,7 +655,7 @@ static int run_forward(Fwd& F, const pf_batch* bt, int max_h_for_dry) {
       TRY(F.gemm(p));
     }
     TRY(F.ln(t1, x, rows, C, e->embed_ln[s], 1e-5f));
-    F.tapf(x, rows * C, "mit.s%d.embed", s + 1);
+    TRY(F.tapf(x, rows * C, "mit.s%d.embed", s + 1));
     for (int i = 0; i < kMitDepths[s]; ++i) {
       const MitBlockW& b = e->blocks[s][i];
       // x = x + attn(norm1(x))
@@ -656,16 +671,16 @@ static int run_forward(Fwd& F, const pf_batch* bt, int max_h_for_dry) {
       }
       if (!dry) LAUNCHED(attention_launch(q, kv, a, n, N, C, heads, st));
       TRY(F.linear(a, rows, C, b.proj, C, x, 0, x));
-      F.tapf(x, rows * C, "mit.s%d.b%d.attn", s + 1, i);
+      TRY(F.tapf(x, rows * C, "mit.s%d.b%d.attn", s + 1, i));
       // x = x + mlp(norm2(x))
       TRY(F.ln(x, t1, rows, C, b.ln2, 1e-6f));
       TRY(F.linear(t1, rows, C, b.fc1, 4 * C, h1));
       if (!dry) LAUNCHED((dwconv3x3_gelu_kernel<<<ew_grid((long long)n * R * ((R + 3) / 4) * C), 256, 0, st>>>(h1, h2, n, R, R, 4 * C, b.dw_w, b.dw_b), cudaGetLastError()));
       TRY(F.linear(h2, rows, 4 * C, b.fc2, C, x, 0, x));
-      F.tapf(x, rows * C, "mit.s%d.b%d", s + 1, i);
+      TRY(F.tapf(x, rows * C, "mit.s%d.b%d", s + 1, i));
     }
     TRY(F.ln(x, cfeat[s], rows, C, e->stage_norm[s], 1e-6f));
-    F.tapf(cfeat[s], rows * C, "mit.c%d", s + 1);
+    TRY(F.tapf(cfeat[s], rows * C, "mit.c%d", s + 1));
     ar.release(m);
   }
 
@@ -685,7 +700,7 @@ static int run_forward(Fwd& F, const pf_batch* bt, int max_h_for_dry) {
         ConvGemmParams p = Fwd::base(cfeat[lvl - 1], Cin, n, r, r, Cin, 3, 1, 1, e->proc[lvl - 1], 512, t, 512);
         p.bias_mode = 2;
         TRY(F.gemm(p));
-        F.tapf(t, px * 512, "head.proc%d", lvl);
+        TRY(F.tapf(t, px * 512, "head.proc%d", lvl));
       }
       auto rcu_conv = [&](const float* A, const GemmW& w, float* Cout, int act, const float* res, int res_relu, const float* res2) {
         ConvGemmParams p = Fwd::base(A, 512, n, r, r, 256, 3, 1, 1, w, 256, Cout, 512);
@@ -710,7 +725,7 @@ static int run_forward(Fwd& F, const pf_batch* bt, int max_h_for_dry) {
       float* up = ar.f(px * 4 * 512);
       if (!dry) LAUNCHED((upsample2x_kernel<<<ew_grid(px * 4 * 64), 256, 0, st>>>(w2, 512, 0, up, 512, 0, n, r, r, 512), cudaGetLastError()));
       fused = up;
-      F.tapf(up, px * 4 * 512, "head.fusion%d", lvl);
+      TRY(F.tapf(up, px * 4 * 512, "head.fusion%d", lvl));
     }
     // conv_fuse_conv0 on cat([fused, ll]) (gravity_head.py:170-171), both heads
     float* c0 = ar.f((long long)n * 160 * 160 * 128);
@@ -720,7 +735,7 @@ static int run_forward(Fwd& F, const pf_batch* bt, int max_h_for_dry) {
       p.act = 1;
       p.groups = 2; p.a_gcoff = 256; p.c_gcoff = 64; p.w_gstride = 64LL * 2880; p.bias_gstride = 64;
       TRY(F.gemm(p));
-      F.tap("head.conv0", c0, (long long)n * 160 * 160 * 128);
+      TRY(F.tap("head.conv0", c0, (long long)n * 160 * 160 * 128));
     }
     float* c0u = ar.f((long long)n * kNet * kNet * 128);
     if (!dry) LAUNCHED((upsample2x_kernel<<<ew_grid((long long)n * kNet * kNet * 16), 256, 0, st>>>(c0, 128, 0, c0u, 128, 0, n, 160, 160, 128), cudaGetLastError()));
@@ -729,7 +744,7 @@ static int run_forward(Fwd& F, const pf_batch* bt, int max_h_for_dry) {
       p.act = 1;
       p.groups = 2; p.a_gcoff = 64; p.c_gcoff = 32; p.w_gstride = 32LL * 576; p.bias_gstride = 32;
       TRY(F.gemm(p));
-      F.tap("head.conv1", conv1_out, (long long)n * kNet * kNet * 64);
+      TRY(F.tap("head.conv1", conv1_out, (long long)n * kNet * kNet * 64));
     }
     ar.release(m);
   }
@@ -770,7 +785,7 @@ static int run_forward(Fwd& F, const pf_batch* bt, int max_h_for_dry) {
         TRY(F.linear(y, rows, C, b.pw1, 4 * C, h, 2));
         TRY(F.linear(h, rows, 4 * C, b.pw2, C, x, 0, x, b.gamma));
       }
-      F.tapf(x, rows * C, "cnx.s%d", s);
+      TRY(F.tapf(x, rows * C, "cnx.s%d", s));
     }
     if (!dry) {
       if (!bt->params) return fail(PF_ERR_ARG, "params output is NULL");
@@ -796,7 +811,7 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
 
   float* x0; PreImage* d_pre; PostImage* d_post;
   TRY(fwd_preprocess(F, bt, x0, d_pre, d_post));
-  F.tap("pre", x0, (long long)n * kNet * kNet * 4);
+  TRY(F.tap("pre", x0, (long long)n * kNet * kNet * 4));
 
   SplitT cfeat[4];
   for (int s = 0; s < 4; ++s) cfeat[s] = F.salloc((long long)n * kMitRes[s] * kMitRes[s], kMitDims[s]);
@@ -843,7 +858,7 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
       TRY(F.tconv_gather(cfeat[s - 1], n, kMitRes[s - 1], kMitRes[s - 1], kMitDims[s - 1], 3, 2, 1, e->embed[s], C, o));
     }
     TRY(F.ln(tf, x, rows, C, e->embed_ln[s], 1e-5f));
-    F.tapf(x, rows * C, "mit.s%d.embed", s + 1);
+    TRY(F.tapf(x, rows * C, "mit.s%d.embed", s + 1));
     for (int i = 0; i < kMitDepths[s]; ++i) {
       const MitBlockW& b = e->blocks[s][i];
       TRY(F.ln_split(x, t1, rows, C, b.ln1, 1e-6f));
@@ -858,12 +873,12 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
       }
       if (!dry) LAUNCHED(e->use_attn_mma ? attention_mma_launch(q, kv, nullptr, n, N, C, heads, st, a) : attention_launch(q, kv, nullptr, n, N, C, heads, st, a));
       { Epi o; o.C = x; o.ldc = C; o.res = x; o.ldr = C; TRY(F.tgemm(a, rows, C, 0, b.proj, C, o)); }
-      F.tapf(x, rows * C, "mit.s%d.b%d.attn", s + 1, i);
+      TRY(F.tapf(x, rows * C, "mit.s%d.b%d.attn", s + 1, i));
       TRY(F.ln_split(x, t1, rows, C, b.ln2, 1e-6f));
       { Epi o; o.C = h1; o.ldc = 4 * C; TRY(F.tgemm(t1, rows, C, 0, b.fc1, 4 * C, o)); }
       if (!dry) LAUNCHED((dwconv3x3_gelu_kernel<<<ew_grid((long long)n * R * ((R + 3) / 4) * C), 256, 0, st>>>(h1, nullptr, n, R, R, 4 * C, b.dw_w, b.dw_b, h2.hi, h2.lo), cudaGetLastError()));
       { Epi o; o.C = x; o.ldc = C; o.res = x; o.ldr = C; TRY(F.tgemm(h2, rows, 4 * C, 0, b.fc2, C, o)); }
-      F.tapf(x, rows * C, "mit.s%d.b%d", s + 1, i);
+      TRY(F.tapf(x, rows * C, "mit.s%d.b%d", s + 1, i));
     }
     TRY(F.ln_split(x, cfeat[s], rows, C, e->stage_norm[s], 1e-6f));
     { char nm[32]; snprintf(nm, sizeof nm, "mit.c%d", s + 1); TRY(F.tap_split(nm, cfeat[s], rows * C)); }
@@ -872,6 +887,7 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
 
   // ---------------- decoder heads (group 0 = gravity, group 1 = latitude, side by side in the channel dimension) ----
   float* conv1_out = ar.f((long long)n * kNet * kNet * 64);
+  bool fuse_pred = false;
   {
     const long long m = ar.mark();
     float* fused = nullptr;       // fp32 top-down feature of the previous level, upsampled to this level's resolution
@@ -888,7 +904,7 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
       {   // composed linear_c{lvl} o linear_c{lvl}_proc (both heads: N = 512), border-class bias
         Epi o; o.C = t; o.ldc = 512; o.S = rt; o.split_relu = 1; o.bias_mode = 2;
         TRY(F.thalo(cfeat[lvl - 1], 0, 0, nullptr, 0, 0, n, r, r, Cin, e->proc[lvl - 1], 512, 1, 0, o));
-        F.tapf(t, px * 512, "head.proc%d", lvl);
+        TRY(F.tapf(t, px * 512, "head.proc%d", lvl));
       }
       auto rcu = [&](const SplitT& A, const GemmW& w, Epi o) {
         o.c_gcoff = 256; o.s_gcoff = 256; o.r_gcoff = 256; o.r2_gcoff = 256;
@@ -908,7 +924,7 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
         float* up = ar.f(px * 4 * 512);
         if (!dry) LAUNCHED((upsample2x_kernel<<<ew_grid(px * 4 * 64), 256, 0, st>>>(w2, 512, 0, up, 512, 0, n, r, r, 512), cudaGetLastError()));
         fused = up;
-        F.tapf(up, px * 4 * 512, "head.fusion%d", lvl);
+        TRY(F.tapf(up, px * 4 * 512, "head.fusion%d", lvl));
       } else {
         fused_s = F.salloc(px * 4, 512);
         if (!dry) LAUNCHED((upsample2x_kernel<<<ew_grid(px * 4 * 64), 256, 0, st>>>(w2, 512, 0, nullptr, 512, 0, n, r, r, 512, fused_s.hi, fused_s.lo), cudaGetLastError()));
@@ -920,18 +936,24 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
     {
       Epi o; o.C = c0; o.ldc = 128; o.c_gcoff = 64; o.act = 1;
       TRY(F.thalo(fused_s, 0, 256, &ll, 256, 0, n, 160, 160, 320, e->conv0, 64, 2, 64, o));
-      F.tap("head.conv0", c0, (long long)n * 160 * 160 * 128);
+      TRY(F.tap("head.conv0", c0, (long long)n * 160 * 160 * 128));
     }
     SplitT c0u = F.salloc((long long)n * kNet * kNet, 128);
     if (!dry) LAUNCHED((upsample2x_kernel<<<ew_grid((long long)n * kNet * kNet * 16), 256, 0, st>>>(c0, 128, 0, nullptr, 128, 0, n, 160, 160, 128, c0u.hi, c0u.lo), cudaGetLastError()));
+    // regression heads: the 1x1 prediction conv + normalise / clamp run inside conv_fuse_conv1's epilogue (conv1's own output is
+    // then only materialised for the debug taps); classification heads (73 / 180 logits) keep the separate tail kernel
+    fuse_pred = D.gravity_classes == 2 && D.latitude_classes == 1;
     {
-      Epi o; o.C = conv1_out; o.ldc = 64; o.c_gcoff = 32; o.act = 1;
-      TRY(F.thalo(c0u, 0, 64, nullptr, 0, 0, n, kNet, kNet, 64, e->conv1, 32, 2, 32, o));
-      F.tap("head.conv1", conv1_out, (long long)n * kNet * kNet * 64);
+      Epi o; o.ldc = 64; o.c_gcoff = 32; o.act = 1;
+      const bool keep_conv1 = !fuse_pred || e->debug;   // (not `o.C != nullptr`: the sizing dry run has null pointers)
+      if (keep_conv1) o.C = conv1_out;
+      PredTail pt[2] = {{e->pred_g_w, e->pred_g_b, dry ? nullptr : bt->pred_gravity, 2, 1}, {e->pred_l_w, e->pred_l_b, dry ? nullptr : bt->pred_latitude, 1, 2}};
+      TRY(F.thalo(c0u, 0, 64, nullptr, 0, 0, n, kNet, kNet, 64, e->conv1, 32, 2, 32, o, fuse_pred ? pt : nullptr));
+      if (keep_conv1) TRY(F.tap("head.conv1", conv1_out, (long long)n * kNet * kNet * 64));
     }
     ar.release(m);
   }
-  TRY(fwd_tails_post(F, bt, conv1_out, d_post));
+  TRY(fwd_tails_post(F, bt, conv1_out, d_post, fuse_pred));
 
   // ---------------- ParamNet (ConvNeXt-T on the predicted fields) -------------------------------------------
   if (D.param_net != PF_PARAM_NONE) {
@@ -965,7 +987,7 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
         { Epi o; o.S = h; o.act = 2; TRY(F.tgemm(y, rows, C, 0, b.pw1, 4 * C, o)); }
         { Epi o; o.C = x; o.ldc = C; o.res = x; o.ldr = C; o.gamma = b.gamma; TRY(F.tgemm(h, rows, 4 * C, 0, b.pw2, C, o)); }
       }
-      F.tapf(x, rows * C, "cnx.s%d", s);
+      TRY(F.tapf(x, rows * C, "cnx.s%d", s));
     }
     if (!dry) {
       if (!bt->params) return fail(PF_ERR_ARG, "params output is NULL");

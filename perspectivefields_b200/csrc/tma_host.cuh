@@ -83,8 +83,10 @@ inline int tma_pick_bn(int N, int mode) {
 // hold the A tile and whose epilogue staging takes 72 KB: BN <= 64), else 32
 inline int tma_pick_kb(int bn, int K, int mode) { return (bn <= (mode == MODE_HALO ? 128 : 64) && K % 64 == 0) ? 64 : 32; }
 
+struct PredTail { const float* w; const float* b; float* out; int nc, mode; };   // per group, see TmaGemmParams::pred_*
+
 template <int BN, int MODE, int KB>
-inline cudaError_t gemm_tma_launch_bn(const TmaMaps& maps, const TmaGemmParams& p, int sm_count, cudaStream_t st) {
+inline cudaError_t gemm_tma_launch_bn(const TmaMaps& maps, const TmaGemmParams& p, int sm_count, cudaStream_t st, const PredTail* pred) {
   using Cfg = TmaCfg<BN, MODE, KB>;
   static bool configured = false;
   if (!configured) {
@@ -108,6 +110,7 @@ inline cudaError_t gemm_tma_launch_bn(const TmaMaps& maps, const TmaGemmParams& 
         q.c_coff = p.c_coff + g * p.c_gcoff; q.s_coff = p.s_coff + g * p.s_gcoff;
         q.r_coff = p.r_coff + g * p.r_gcoff; q.r2_coff = p.r2_coff + g * p.r2_gcoff;
         q.b_row0 = g * p.N;
+        if (pred) { q.pred_w = pred[g].w; q.pred_b = pred[g].b; q.pred_out = pred[g].out; q.pred_nc = pred[g].nc; q.pred_mode = pred[g].mode; }
         if (cdiv(p.N, BN) > 1) return cudaErrorInvalidValue;   // (not needed by the network: conv_fuse_conv1 has N = 32)
         const unsigned gr = (unsigned)(m_tiles < sm_count ? m_tiles : sm_count);
         gemm_tma_kernel<BN, MODE, KB><<<gr, kTmaThreads, Cfg::kSmemBytes, st>>>(maps, q, tiles_x, tiles_y);
@@ -116,12 +119,14 @@ inline cudaError_t gemm_tma_launch_bn(const TmaMaps& maps, const TmaGemmParams& 
       }
     return last;
   }
+  if (pred) return cudaErrorInvalidValue;   // the fused prediction tail exists for the resident-weight N = 32 launches only
   gemm_tma_kernel<BN, MODE, KB><<<grid, kTmaThreads, Cfg::kSmemBytes, st>>>(maps, p, tiles_x, tiles_y);
   return cudaGetLastError();
 }
 
-inline cudaError_t gemm_tma_launch(int mode, const TmaMaps& maps, const TmaGemmParams& p, int bn, int kb, int sm_count, cudaStream_t st) {
-#define PF_TMA_CASE(BN_, MODE_, KB_) if (bn == BN_ && kb == KB_) return gemm_tma_launch_bn<BN_, MODE_, KB_>(maps, p, sm_count, st)
+inline cudaError_t gemm_tma_launch(int mode, const TmaMaps& maps, const TmaGemmParams& p, int bn, int kb, int sm_count, cudaStream_t st,
+                                   const PredTail* pred = nullptr) {
+#define PF_TMA_CASE(BN_, MODE_, KB_) if (bn == BN_ && kb == KB_) return gemm_tma_launch_bn<BN_, MODE_, KB_>(maps, p, sm_count, st, pred)
   if (mode == MODE_GEMM) {
     PF_TMA_CASE(256, MODE_GEMM, 32); PF_TMA_CASE(224, MODE_GEMM, 32); PF_TMA_CASE(192, MODE_GEMM, 32); PF_TMA_CASE(160, MODE_GEMM, 32);
     PF_TMA_CASE(128, MODE_GEMM, 32); PF_TMA_CASE(96, MODE_GEMM, 32); PF_TMA_CASE(64, MODE_GEMM, 32); PF_TMA_CASE(32, MODE_GEMM, 32);
