@@ -16,6 +16,7 @@ inside the timed region vs the measured bf16 peak, cpu_baseline = the oracle por
 """
 import argparse
 import ctypes
+import gc
 import json
 import os
 import subprocess
@@ -186,6 +187,9 @@ def main():
     B = args.batch
     imgs = wg.synth_images(B, H, W, seed=1000 + rank)  # each rank owns its shard of the global batch
     eng = model._get_engine()
+    for kv in filter(None, os.environ.get("PF_BENCH_OPTS", "").split(",")):   # A/B runs of engine options, e.g. PF_BENCH_OPTS=phase_conv1=0
+        k, v = kv.split("=")
+        model.set_option(k, int(v))
     L = _native.lib()
     heights, widths = [H] * B, [W] * B
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > L2 (126 MB)
@@ -193,20 +197,42 @@ def main():
     # ---------------- leg 1: inputs resident in HBM ("value") ------------------------------------------------
     blob, offsets = eng.stage_images(imgs)
     torch.cuda.synchronize(dev)
-    for _ in range(args.warmup):
-        eng.forward(B, heights, widths, blob=blob, offsets=offsets)
+    sampler = ClockSampler(local)   # NVML is initialised before the warm-up: its start-up must not leave the GPU idle in front of the timed steps
+    out = None
+    for _ in range(args.warmup):    # same sequence as a timed step (flush, forward, result rebinding)
+        flush.fill_(1)
+        out = eng.forward(B, heights, widths, blob=blob, offsets=offsets)
+    # the cyclic garbage collector is off inside the timed regions (as timeit does): a generation-2 pass over the interpreter's
+    # ~10^6 objects is a 10-100 ms host stall, longer than the two steps of work the launch queue holds
+    gc.collect()
+    gc.disable()
     barrier()
-    sampler = ClockSampler(local)
     launches0 = L.pf_kernel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     host_t0 = time.perf_counter()
     host_fwd = 0.0
+    tracing = bool(os.environ.get("PF_BENCH_TRACE"))
+    step_ev, step_host, c_times = [], [], []
+    if tracing:   # per-step GPU / host times and the time inside the C call, to localise sporadic stalls
+        c_forward = eng.L.pf_forward
+
+        def timed_forward(*a):
+            t = time.perf_counter()
+            r_ = c_forward(*a)
+            c_times.append(round((time.perf_counter() - t) * 1000, 2))
+            return r_
+        eng.L.pf_forward = timed_forward
     for _ in range(args.steps):
         flush.fill_(1)  # L2 flush between timed iterations (inside the timed region: ~0.1 ms of ~30)
         h0 = time.perf_counter()
         out = eng.forward(B, heights, widths, blob=blob, offsets=offsets)
         host_fwd += time.perf_counter() - h0
+        if tracing:
+            step_host.append(round((time.perf_counter() - h0) * 1000, 2))
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            step_ev.append(ev)
     e1.record()
     host_enqueue_ms = (time.perf_counter() - host_t0) * 1000 / args.steps
     # clock samples DURING the timed region: the host is ahead of the GPU here (all K steps are queued), so the NVML calls
@@ -216,6 +242,10 @@ def main():
         sampler.sample()
     barrier()
     ms = e0.elapsed_time(e1)
+    if tracing:
+        eng.L.pf_forward = c_forward
+        gpu = [round((e0 if i == 0 else step_ev[i - 1]).elapsed_time(step_ev[i]), 2) for i in range(len(step_ev))]
+        print(f"[rank {rank}] value leg per step: gpu ms {gpu} | host eng.forward ms {step_host} | inside pf_forward ms {c_times}", file=sys.stderr, flush=True)
     launches = L.pf_kernel_launch_count() - launches0
     clocks = sampler.stop()
     # roofline pass: the same K steps again with a CUDA-event pair around every GEMM-engine launch (on the launch stream).
@@ -276,12 +306,18 @@ def main():
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tw = time.perf_counter()
     f0.record()
+    trace = []
     for _ in range(args.steps):
+        ts = time.perf_counter()
         e2e_step()
+        trace.append(round((time.perf_counter() - ts) * 1000, 2))
+    if os.environ.get("PF_BENCH_TRACE"):
+        print(f"[rank {rank}] e2e host ms per step: {trace}", file=sys.stderr, flush=True)
     torch.cuda.current_stream(dev).wait_stream(copy_stream)   # the last read-back is inside the timed region
     f1.record()
     barrier()
     wall_ms = (time.perf_counter() - tw) * 1000
+    gc.enable()
     t = torch.tensor([max(f0.elapsed_time(f1), wall_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

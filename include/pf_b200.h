@@ -103,7 +103,9 @@ int pf_profile_read(pf_handle h, double* out21);
  * "tcgen05" (default 1) selects the register-staged tcgen05 kernels over the warp-level HMMA kernel, "halo3x3" (default 1)
  * the halo-tile variant for 3x3/stride-1 convolutions.  All engines evaluate the same bf16x3 products.
  * "attn_mma" (default 1, TMA graph only): attention core on the tensor cores (attention_mma.cuh) instead of CUDA cores.
- * "stem_tc" (default 1, TMA graph only): the two 7x7 stems as patch gather + TMA GEMM instead of fp32 direct convolution. */
+ * "stem_tc" (default 1, TMA graph only): the two 7x7 stems as patch gather + TMA GEMM instead of fp32 direct convolution.
+ * "phase_conv1" (default 1, TMA graph only): conv_fuse_conv1 composed with the x2 bilinear upsample in front of it (four output
+ *   phases on the 160x160 grid + an exact fp32 border-ring kernel); 0 = materialise the upsampled tensor, conv at 320x320. */
 int pf_set_option(pf_handle h, const char* name, int value);
 
 /* Debug taps (tests only): when enabled, intermediates of the next pf_forward are kept (never recycled) and can be

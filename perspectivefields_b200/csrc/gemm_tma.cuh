@@ -49,6 +49,10 @@ struct TmaGemmParams {
   // latitude_head.py:174) + F.normalize (pred_mode 1, gravity_head.py:192-193) or clamp to [-1,1] (pred_mode 2,
   // latitude_head.py:191-192), written NCHW to pred_out; replaces the separate pred_tail_kernel pass over conv1's output
   const float* pred_w; const float* pred_b; float* pred_out; int pred_nc, pred_mode;
+  // MODE_HALO, N = BN = 128: the four 32-column chunks are the four output phases (py, px) of a convolution composed with the
+  // bilinear x2 upsample in front of it (weights.py:_compose_up2_conv3): chunk ph, low-res pixel (y, x) -> pixel
+  // (2y + ph/2, 2x + ph%2) of the 2H x 2W output, 32 channels.  C / S / the prediction tail are addressed on that grid.
+  int phase4;
 };
 
 // KB = K elements per pipeline step: 32 (64 B rows, SWIZZLE_64B) for wide tiles, 64 (128 B rows, SWIZZLE_128B) for BN <= 128
@@ -401,12 +405,14 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
       long long m;
       bool valid;
       int cls_off = 0;
+      int bimg = 0, oy = 0, ox = 0;
       if (MODE == MODE_GEMM) {
         m = (long long)mt * 128 + r;
         valid = m < p.M;
       } else {
-        const int tx = mt % tiles_x, ty = (mt / tiles_x) % tiles_y, bimg = mt / (tiles_x * tiles_y);
-        const int oy = ty * kHtTileH + (r >> 3), ox = tx * kHtTileW + (r & 7);
+        const int tx = mt % tiles_x, ty = (mt / tiles_x) % tiles_y;
+        bimg = mt / (tiles_x * tiles_y);
+        oy = ty * kHtTileH + (r >> 3); ox = tx * kHtTileW + (r & 7);
         valid = oy < p.H && ox < p.W;
         m = ((long long)bimg * p.H + oy) * p.W + ox;
         if (p.bias_mode == 2) {
@@ -423,6 +429,10 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
         uint32_t v[32];
         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + ch * 32), v);
         const int nb = n0 + ch * 32;
+        const bool ph4 = MODE == MODE_HALO && BN == 128 && p.phase4;
+        // output row / first output column of this chunk (phase mode: hi-res pixel of phase `ch`, channels 0-31)
+        const long long mo = ph4 ? ((long long)bimg * 2 * p.H + 2 * oy + (ch >> 1)) * (2 * p.W) + 2 * ox + (ch & 1) : m;
+        const int nbo = ph4 ? 0 : nb;
         if (valid && nb < p.N) {
           float o[32];
 #pragma unroll
@@ -465,7 +475,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
               o[j] += rv.x; o[j + 1] += rv.y; o[j + 2] += rv.z; o[j + 3] += rv.w;
             }
           }
-          if (MODE == MODE_HALO && BN == 32 && p.pred_w) {
+          if (MODE == MODE_HALO && (BN == 32 || BN == 128) && p.pred_w) {
             float v0 = __ldg(p.pred_b), v1 = p.pred_nc > 1 ? __ldg(p.pred_b + 1) : 0.f;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -476,8 +486,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
                 v1 = fmaf(o[j], w1.x, v1); v1 = fmaf(o[j + 1], w1.y, v1); v1 = fmaf(o[j + 2], w1.z, v1); v1 = fmaf(o[j + 3], w1.w, v1);
               }
             }
-            const long long HWl = (long long)p.H * p.W;
-            const long long bi = m / HWl, pix = m - bi * HWl;
+            const long long HWl = (long long)p.H * p.W * (ph4 ? 4 : 1);
+            const long long bi = mo / HWl, pix = mo - bi * HWl;
             float* po = p.pred_out + bi * p.pred_nc * HWl + pix;
             if (p.pred_mode == 1) {
               const float nrm = fmaxf(sqrtf(v0 * v0 + v1 * v1), 1e-12f);
@@ -487,12 +497,12 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
             }
           }
           if (p.C) {
-            float* cp = p.C + m * p.ldc + p.c_coff + g * p.c_gcoff + nb;
+            float* cp = p.C + mo * p.ldc + p.c_coff + g * p.c_gcoff + nbo;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
           }
           if (p.Shi) {
-            const long long so = m * p.lds + p.s_coff + g * p.s_gcoff + nb;
+            const long long so = mo * p.lds + p.s_coff + g * p.s_gcoff + nbo;
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               uint4 h, l;

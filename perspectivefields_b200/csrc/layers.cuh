@@ -471,6 +471,129 @@ __global__ void __launch_bounds__(128) pred_tail_kernel(const float* __restrict_
   }
 }
 
+// =====================================================================================================
+// Border ring of conv_fuse_conv1 (gravity_head.py:171-175 / latitude_head.py:170-174).  The engine evaluates
+// conv3x3(bilinear_x2(c0)) as four phase convolutions on the 160x160 grid (weights.py:_compose_up2_conv3); that identity holds
+// wherever neither the upsample's index clamp nor the convolution's zero padding is involved, i.e. everywhere except the two
+// outermost rows / columns of the 320x320 output.  This kernel recomputes those 2544 pixels per image directly in fp32:
+// u = bilinear_x2(c0) sampled on the fly (align_corners=False: src = max(0, (i + 0.5) / 2 - 0.5), neighbour index clamped),
+// zero outside the image, 3x3 taps, + bias, ReLU; then (regression heads) the same fused prediction tail as the GEMM epilogue.
+// c0: split planes [B, H, W, 128] (gravity channels 0-63, latitude 64-127); wf: [2][9][64][32] fp32; out NHWC [B, 2H, 2W, 64].
+// Block = 64 ring pixels x both heads; warp w -> head w / 4, output channels (w % 4) * 8 .. + 8; lane -> pixels lane, lane + 32.
+constexpr int kRingPx = 64;
+__host__ __device__ inline int conv1_ring_count(int H2, int W2) { return 4 * W2 + 4 * (H2 - 4); }
+__global__ void __launch_bounds__(256) conv1_ring_kernel(const __nv_bfloat16* __restrict__ chi, const __nv_bfloat16* __restrict__ clo, int H, int W,
+                                                         const float* __restrict__ wf, const float* __restrict__ bias, float* __restrict__ out,
+                                                         const float* __restrict__ pg_w, const float* __restrict__ pg_b, float* __restrict__ pg_out,
+                                                         const float* __restrict__ pl_w, const float* __restrict__ pl_b, float* __restrict__ pl_out) {
+  extern __shared__ __align__(16) float s_ring[];
+  float* sU = s_ring;                        // [128 ch][64 px]
+  float* sW = s_ring + 128 * kRingPx;        // [2][64 ci][32 o]
+  float* sP = sW + 2 * 64 * 32;              // [64 px][3 outputs][4 channel quarters]
+  __shared__ int s_y[kRingPx], s_x[kRingPx];
+  const int H2 = 2 * H, W2 = 2 * W, ring = conv1_ring_count(H2, W2);
+  const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < kRingPx) {
+    const int r = blockIdx.x * kRingPx + tid;
+    int y = -1, x = -1;
+    if (r < 4 * W2) { const int k = r / W2; y = k < 2 ? k : H2 - 4 + k; x = r - k * W2; }
+    else if (r < ring) { const int q = r - 4 * W2, k = q & 3; y = 2 + (q >> 2); x = k < 2 ? k : W2 - 4 + k; }
+    s_y[tid] = y; s_x[tid] = x;
+  }
+  const int g = warp >> 2, oq = warp & 3;
+  float acc[2][8];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  for (int tap = 0; tap < 9; ++tap) {
+    __syncthreads();
+    // weights of this tap: [2][64][32] <- wf[g][tap][ci][o]
+    for (int i = tid; i < 2 * 64 * 8; i += 256) {
+      const int gg = i / 512, rem = i % 512;
+      reinterpret_cast<float4*>(sW)[i] = __ldg(reinterpret_cast<const float4*>(wf + ((long long)(gg * 9 + tap) * 64) * 32) + rem);
+    }
+    // upsampled input of this tap: 64 px x 16 channel octets
+    const int ky = tap / 3 - 1, kx = tap % 3 - 1;
+    for (int i = tid; i < kRingPx * 16; i += 256) {
+      const int px = i & (kRingPx - 1), c8 = i / kRingPx;
+      const int y = s_y[px] + ky, x = s_x[px] + kx;
+      float u[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) u[e] = 0.f;
+      if (s_y[px] >= 0 && y >= 0 && y < H2 && x >= 0 && x < W2) {
+        const float sy = fmaxf((y + 0.5f) * 0.5f - 0.5f, 0.f), sx = fmaxf((x + 0.5f) * 0.5f - 0.5f, 0.f);
+        const int y0 = (int)sy, x0 = (int)sx;
+        const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+        const float ly = sy - y0, lx = sx - x0;
+        const float cw[4] = {(1.f - ly) * (1.f - lx), (1.f - ly) * lx, ly * (1.f - lx), ly * lx};
+        const int yy[4] = {y0, y0, y1, y1}, xx[4] = {x0, x1, x0, x1};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const long long o = (((long long)b * H + yy[k]) * W + xx[k]) * 128 + c8 * 8;
+          const uint4 h = __ldg(reinterpret_cast<const uint4*>(chi + o)), l = __ldg(reinterpret_cast<const uint4*>(clo + o));
+          const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float v0 = __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
+            const float v1 = __uint_as_float(hw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
+            u[2 * e] = fmaf(cw[k], v0, u[2 * e]); u[2 * e + 1] = fmaf(cw[k], v1, u[2 * e + 1]);
+          }
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sU[(c8 * 8 + e) * kRingPx + px] = u[e];
+    }
+    __syncthreads();
+    const float* su = sU + g * 64 * kRingPx;
+    const float* sw = sW + g * 64 * 32 + oq * 8;
+#pragma unroll 4
+    for (int ci = 0; ci < 64; ++ci) {
+      const float u0 = su[ci * kRingPx + lane], u1 = su[ci * kRingPx + lane + 32];
+      const float4 w0 = *reinterpret_cast<const float4*>(sw + ci * 32), w1 = *reinterpret_cast<const float4*>(sw + ci * 32 + 4);
+      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { acc[0][j] = fmaf(u0, wv[j], acc[0][j]); acc[1][j] = fmaf(u1, wv[j], acc[1][j]); }
+    }
+  }
+  // bias + ReLU, conv1 output (when kept), partial prediction dots
+  const float* pw = g == 0 ? pg_w : pl_w;
+  const int pnc = g == 0 ? 2 : 1;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int px = lane + 32 * i, y = s_y[px], x = s_x[px];
+    float p0 = 0.f, p1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int o = oq * 8 + j;
+      acc[i][j] = fmaxf(acc[i][j] + __ldg(bias + g * 32 + o), 0.f);
+      if (pw) { p0 = fmaf(acc[i][j], __ldg(pw + o), p0); if (pnc > 1) p1 = fmaf(acc[i][j], __ldg(pw + 32 + o), p1); }
+    }
+    if (y >= 0 && out) {
+      float* op = out + (((long long)b * H2 + y) * W2 + x) * 64 + g * 32 + oq * 8;
+      *reinterpret_cast<float4*>(op) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      *reinterpret_cast<float4*>(op + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+    }
+    if (pw) {
+      if (g == 0) { sP[(px * 3 + 0) * 4 + oq] = p0; sP[(px * 3 + 1) * 4 + oq] = p1; }
+      else sP[(px * 3 + 2) * 4 + oq] = p0;
+    }
+  }
+  if (!pg_w) return;
+  __syncthreads();
+  if (tid < kRingPx && s_y[tid] >= 0) {
+    const float* q = sP + tid * 12;
+    const long long HW2 = (long long)H2 * W2, pix = (long long)s_y[tid] * W2 + s_x[tid];
+    const float v0 = __ldg(pg_b) + ((q[0] + q[1]) + (q[2] + q[3])), v1 = __ldg(pg_b + 1) + ((q[4] + q[5]) + (q[6] + q[7]));
+    const float vl = __ldg(pl_b) + ((q[8] + q[9]) + (q[10] + q[11]));
+    const float nrm = fmaxf(sqrtf(v0 * v0 + v1 * v1), 1e-12f);
+    float* po = pg_out + (long long)b * 2 * HW2 + pix;
+    po[0] = v0 / nrm; po[HW2] = v1 / nrm;
+    pl_out[(long long)b * HW2 + pix] = fminf(fmaxf(vl, -1.f), 1.f);
+  }
+}
+constexpr int kRingSmem = (128 * kRingPx + 2 * 64 * 32 + kRingPx * 12) * 4;
+
 // Classification variant: argmax over channels + bin decode (gravity_head.py:243-244 + utils.py:114-130;
 // latitude_head.py:205-208 + utils.py:148-162).  logits NCHW [B, NC, HW] -> field [B, 2 or 1, HW].
 // torch.argmax returns the FIRST maximal index; strict '>' reproduces that.

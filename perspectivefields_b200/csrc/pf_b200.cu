@@ -112,6 +112,9 @@ struct pf_engine {
   GemmW proc[4];   // composed linear_c{l} o linear_c{l}_proc, both heads side by side (N = 512), index lvl-1
   GemmW rcu[4][2][2];  // [fusion-1][unit-1][conv-1], grouped over the two heads
   GemmW conv0, conv1;
+  GemmW conv1p;                       // conv_fuse_conv1 composed with the x2 upsample in front of it: 4 phases x 32 outputs per head
+  const float *conv1f_w, *conv1f_b;   // plain fp32 conv_fuse_conv1 [head][tap][ci][o] / bias, for the border-ring kernel
+  bool use_phase = true;              // option "phase_conv1": 0 = materialise the upsampled tensor and run conv1 at 320x320
   const float *pred_g_w, *pred_g_b, *pred_l_w, *pred_l_b;
   const float *pn_stem_w, *pn_stem_b;
   LnW pn_stem_ln, pn_ds_ln[4], pn_norm;
@@ -226,6 +229,9 @@ static int resolve_weights(pf_engine* e) {
     }
   TRY(get_gemm(e, "head.conv0", 64, 9 * 320, 64, &e->conv0, 2));
   TRY(get_gemm(e, "head.conv1", 32, 9 * 64, 32, &e->conv1, 2));
+  TRY(get_gemm(e, "head.conv1p", 128, 9 * 64, 128, &e->conv1p, 2));
+  TRY(get_f(e, "head.conv1f.w", 2LL * 9 * 64 * 32, &e->conv1f_w));
+  TRY(get_f(e, "head.conv1f.b", 64, &e->conv1f_b));
   TRY(get_f(e, "head.pred_g.w", 32LL * e->desc.gravity_classes, &e->pred_g_w));
   TRY(get_f(e, "head.pred_g.b", e->desc.gravity_classes, &e->pred_g_b));
   TRY(get_f(e, "head.pred_l.w", 32LL * e->desc.latitude_classes, &e->pred_l_w));
@@ -383,6 +389,7 @@ struct Fwd {
     const float* res = nullptr; int ldr = 0, r_coff = 0, r_gcoff = 0, res_relu = 0;
     const float* res2 = nullptr; int ldr2 = 0, r2_coff = 0, r2_gcoff = 0;
     int bias_mode = 1;
+    int phase4 = 0;   // halo mode, N = 128: columns are 4 output phases x 32 channels of a 2H x 2W output (TmaGemmParams::phase4)
   };
   static void fill_epi(TmaGemmParams& p, const GemmW& w, const Epi& o, int bias_gstride) {
     p.bias = w.b; p.bias_mode = w.b ? o.bias_mode : 0; p.bias_gstride = bias_gstride;
@@ -391,6 +398,7 @@ struct Fwd {
     p.res2 = o.res2; p.ldr2 = o.ldr2; p.r2_coff = o.r2_coff; p.r2_gcoff = o.r2_gcoff;
     p.C = o.C; p.ldc = o.ldc; p.c_coff = o.c_coff; p.c_gcoff = o.c_gcoff;
     p.Shi = o.S.hi; p.Slo = o.S.lo; p.lds = o.S.ld; p.s_coff = o.s_coff; p.s_gcoff = o.s_gcoff; p.split_relu = o.split_relu;
+    p.phase4 = o.phase4;
   }
   // cached tensor-map constructors
   template <class F>
@@ -932,25 +940,48 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
       }
     }
     // conv_fuse_conv0 on cat([fused, ll]) -> ReLU ; x2 ; conv_fuse_conv1 -> ReLU
-    float* c0 = ar.f((long long)n * 160 * 160 * 128);
-    {
-      Epi o; o.C = c0; o.ldc = 128; o.c_gcoff = 64; o.act = 1;
-      TRY(F.thalo(fused_s, 0, 256, &ll, 256, 0, n, 160, 160, 320, e->conv0, 64, 2, 64, o));
-      TRY(F.tap("head.conv0", c0, (long long)n * 160 * 160 * 128));
-    }
-    SplitT c0u = F.salloc((long long)n * kNet * kNet, 128);
-    if (!dry) LAUNCHED((upsample2x_kernel<<<ew_grid((long long)n * kNet * kNet * 16), 256, 0, st>>>(c0, 128, 0, nullptr, 128, 0, n, 160, 160, 128, c0u.hi, c0u.lo), cudaGetLastError()));
     // regression heads: the 1x1 prediction conv + normalise / clamp run inside conv_fuse_conv1's epilogue (conv1's own output is
     // then only materialised for the debug taps); classification heads (73 / 180 logits) keep the separate tail kernel
     fuse_pred = D.gravity_classes == 2 && D.latitude_classes == 1;
-    {
-      Epi o; o.ldc = 64; o.c_gcoff = 32; o.act = 1;
-      const bool keep_conv1 = !fuse_pred || e->debug;   // (not `o.C != nullptr`: the sizing dry run has null pointers)
+    const bool keep_conv1 = !fuse_pred || e->debug;   // (not `o.C != nullptr`: the sizing dry run has null pointers)
+    PredTail pt[2] = {{e->pred_g_w, e->pred_g_b, dry ? nullptr : bt->pred_gravity, 2, 1}, {e->pred_l_w, e->pred_l_b, dry ? nullptr : bt->pred_latitude, 1, 2}};
+    if (e->use_phase) {
+      // x2 upsample folded into conv1's weights: conv1 runs on the 160x160 grid with N = 4 output phases x 32 (no upsampled
+      // tensor); the two outermost output rows / columns, where the identity does not hold, are recomputed by conv1_ring_kernel
+      SplitT c0s = F.salloc((long long)n * 160 * 160, 128);
+      {
+        Epi o; o.S = c0s; o.s_gcoff = 64; o.act = 1;
+        TRY(F.thalo(fused_s, 0, 256, &ll, 256, 0, n, 160, 160, 320, e->conv0, 64, 2, 64, o));
+        TRY(F.tap_split("head.conv0", c0s, (long long)n * 160 * 160 * 128));
+      }
+      Epi o; o.ldc = 64; o.c_gcoff = 32; o.act = 1; o.phase4 = 1;
       if (keep_conv1) o.C = conv1_out;
-      PredTail pt[2] = {{e->pred_g_w, e->pred_g_b, dry ? nullptr : bt->pred_gravity, 2, 1}, {e->pred_l_w, e->pred_l_b, dry ? nullptr : bt->pred_latitude, 1, 2}};
+      TRY(F.thalo(c0s, 0, 64, nullptr, 0, 0, n, 160, 160, 64, e->conv1p, 128, 2, 128, o, fuse_pred ? pt : nullptr));
+      if (!dry) {
+        static bool ring_configured = false;
+        if (!ring_configured) {
+          CU(cudaFuncSetAttribute(conv1_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingSmem));
+          ring_configured = true;
+        }
+        const dim3 grid((unsigned)cdiv(conv1_ring_count(kNet, kNet), kRingPx), (unsigned)n);
+        LAUNCHED((conv1_ring_kernel<<<grid, 256, kRingSmem, st>>>(c0s.hi, c0s.lo, 160, 160, e->conv1f_w, e->conv1f_b, keep_conv1 ? conv1_out : nullptr,
+                                                                 fuse_pred ? e->pred_g_w : nullptr, e->pred_g_b, bt->pred_gravity,
+                                                                 fuse_pred ? e->pred_l_w : nullptr, e->pred_l_b, bt->pred_latitude), cudaGetLastError()));
+      }
+    } else {
+      float* c0 = ar.f((long long)n * 160 * 160 * 128);
+      {
+        Epi o; o.C = c0; o.ldc = 128; o.c_gcoff = 64; o.act = 1;
+        TRY(F.thalo(fused_s, 0, 256, &ll, 256, 0, n, 160, 160, 320, e->conv0, 64, 2, 64, o));
+        TRY(F.tap("head.conv0", c0, (long long)n * 160 * 160 * 128));
+      }
+      SplitT c0u = F.salloc((long long)n * kNet * kNet, 128);
+      if (!dry) LAUNCHED((upsample2x_kernel<<<ew_grid((long long)n * kNet * kNet * 16), 256, 0, st>>>(c0, 128, 0, nullptr, 128, 0, n, 160, 160, 128, c0u.hi, c0u.lo), cudaGetLastError()));
+      Epi o; o.ldc = 64; o.c_gcoff = 32; o.act = 1;
+      if (keep_conv1) o.C = conv1_out;
       TRY(F.thalo(c0u, 0, 64, nullptr, 0, 0, n, kNet, kNet, 64, e->conv1, 32, 2, 32, o, fuse_pred ? pt : nullptr));
-      if (keep_conv1) TRY(F.tap("head.conv1", conv1_out, (long long)n * kNet * kNet * 64));
     }
+    if (keep_conv1) TRY(F.tap("head.conv1", conv1_out, (long long)n * kNet * kNet * 64));
     ar.release(m);
   }
   TRY(fwd_tails_post(F, bt, conv1_out, d_post, fuse_pred));
@@ -1104,6 +1135,7 @@ int pf_set_option(pf_handle h, const char* name, int value) {
   if (!strcmp(name, "tma")) { h->use_tma = value != 0; return PF_OK; }
   if (!strcmp(name, "attn_mma")) { h->use_attn_mma = value != 0; return PF_OK; }
   if (!strcmp(name, "stem_tc")) { h->use_stem_tc = value != 0; return PF_OK; }
+  if (!strcmp(name, "phase_conv1")) { h->use_phase = value != 0; return PF_OK; }
   return fail(PF_ERR_ARG, "pf_set_option: unknown option '%s'", name);
 }
 // out[cfg*3 + {0,1,2}] = {milliseconds, algorithmic FLOPs, launches} per GEMM engine configuration (7 configs),

@@ -99,7 +99,8 @@ inline cudaError_t gemm_tma_launch_bn(const TmaMaps& maps, const TmaGemmParams& 
   const long long total = m_tiles * cdiv(p.N, BN) * p.groups;
   const unsigned grid = (unsigned)(total < sm_count ? total : sm_count);
   // resident-weight mode (single chunk, one N tile) assumes every tile of a CTA uses the same weights: one group per launch
-  if (MODE == MODE_HALO && p.Cin == 64 && 9 * (64 / KB) <= Cfg::kStages && (p.groups > 1 || cdiv(p.N, BN) > 1)) {
+  // (a fused prediction tail is per group as well: same decomposition)
+  if (MODE == MODE_HALO && ((p.Cin == 64 && 9 * (64 / KB) <= Cfg::kStages && (p.groups > 1 || cdiv(p.N, BN) > 1)) || pred)) {
     cudaError_t last = cudaSuccess;
     for (int g = 0; g < p.groups; ++g)
       for (int nt = 0; nt < cdiv(p.N, BN); ++nt) {
@@ -111,7 +112,7 @@ inline cudaError_t gemm_tma_launch_bn(const TmaMaps& maps, const TmaGemmParams& 
         q.r_coff = p.r_coff + g * p.r_gcoff; q.r2_coff = p.r2_coff + g * p.r2_gcoff;
         q.b_row0 = g * p.N;
         if (pred) { q.pred_w = pred[g].w; q.pred_b = pred[g].b; q.pred_out = pred[g].out; q.pred_nc = pred[g].nc; q.pred_mode = pred[g].mode; }
-        if (cdiv(p.N, BN) > 1) return cudaErrorInvalidValue;   // (not needed by the network: conv_fuse_conv1 has N = 32)
+        if (cdiv(p.N, BN) > 1) return cudaErrorInvalidValue;   // (not needed by the network: conv_fuse_conv1 has one N tile)
         const unsigned gr = (unsigned)(m_tiles < sm_count ? m_tiles : sm_count);
         gemm_tma_kernel<BN, MODE, KB><<<gr, kTmaThreads, Cfg::kSmemBytes, st>>>(maps, q, tiles_x, tiles_y);
         last = cudaGetLastError();
@@ -119,7 +120,6 @@ inline cudaError_t gemm_tma_launch_bn(const TmaMaps& maps, const TmaGemmParams& 
       }
     return last;
   }
-  if (pred) return cudaErrorInvalidValue;   // the fused prediction tail exists for the resident-weight N = 32 launches only
   gemm_tma_kernel<BN, MODE, KB><<<grid, kTmaThreads, Cfg::kSmemBytes, st>>>(maps, p, tiles_x, tiles_y);
   return cudaGetLastError();
 }

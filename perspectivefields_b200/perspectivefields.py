@@ -48,6 +48,7 @@ class _Engine:
         self.pinned = None
         self.pinned_event = None
         self.dev_blob = None
+        self.staged_slot = None
 
     def close(self):
         if self.handle:
@@ -68,24 +69,40 @@ class _Engine:
         return self.workspace
 
     def stage_images(self, imgs):
-        """Host uint8 images -> one pinned blob -> one async H2D copy.  Returns (device blob, offsets)."""
+        """Host uint8 images -> one pinned blob -> one async H2D copy on a dedicated copy stream (two pinned / device blob pairs,
+        so the upload of batch k+1 overlaps the forward of batch k).  Returns (device blob, offsets); the current stream has been
+        made to wait for the upload."""
         sizes = [im.size for im in imgs]
         offsets = np.zeros(len(imgs), np.int64)
         np.cumsum(sizes[:-1], out=offsets[1:])
         total = int(sum(sizes))
-        if self.pinned is None or self.pinned.numel() < total:
-            self.pinned = torch.empty(max(total, 1 << 20), dtype=torch.uint8).pin_memory()
-            self.dev_blob = torch.empty(self.pinned.numel(), dtype=torch.uint8, device=self.device)
-            self.pinned_event = None
-        if self.pinned_event is not None:
-            self.pinned_event.synchronize()  # the previous batch's H2D must have drained before the blob is reused
-        host = self.pinned.numpy()
+        if self.pinned is None or self.pinned[0].numel() < total:
+            cap = max(total, 1 << 20)
+            self.pinned = [torch.empty(cap, dtype=torch.uint8).pin_memory() for _ in range(2)]
+            self.dev_blob = [torch.empty(cap, dtype=torch.uint8, device=self.device) for _ in range(2)]
+            self.pinned_event = [None, None]    # upload from pinned[s] has completed
+            self.blob_free = [None, None]       # the forward that read dev_blob[s] has completed (recorded by forward())
+            self.h2d_stream = torch.cuda.Stream(device=self.device)
+            self.slot = 0
+        s = self.slot = self.slot ^ 1
+        if self.pinned_event[s] is not None:
+            self.pinned_event[s].synchronize()  # the upload that last used this pinned buffer must have drained before it is rewritten
+        host = self.pinned[s].numpy()
         for im, off in zip(imgs, offsets):
             host[off:off + im.size] = im.reshape(-1)
-        self.dev_blob[:total].copy_(self.pinned[:total], non_blocking=True)
-        self.pinned_event = torch.cuda.Event()
-        self.pinned_event.record()
-        return self.dev_blob, offsets
+        cur = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self.h2d_stream):
+            if self.blob_free[s] is not None:
+                self.h2d_stream.wait_event(self.blob_free[s])
+            else:
+                self.h2d_stream.wait_stream(cur)
+            self.dev_blob[s][:total].copy_(self.pinned[s][:total], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.h2d_stream)
+        self.pinned_event[s] = ev
+        cur.wait_event(ev)
+        self.staged_slot = s
+        return self.dev_blob[s], offsets
 
     def forward(self, n, heights, widths, blob=None, offsets=None, chw=None):
         dev = self.device
@@ -121,6 +138,10 @@ class _Engine:
         bt.params = out["params"].data_ptr()
         stream = torch.cuda.current_stream(dev).cuda_stream
         _native.check(self.L.pf_forward(self.handle, ctypes.byref(bt), ws.data_ptr(), ws.numel(), stream))
+        if blob is not None and self.staged_slot is not None and self.dev_blob is not None and blob is self.dev_blob[self.staged_slot]:
+            ev = torch.cuda.Event()
+            ev.record()
+            self.blob_free[self.staged_slot] = ev   # stage_images may overwrite this device blob once the forward has read it
         return out
 
 

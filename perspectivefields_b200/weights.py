@@ -64,6 +64,21 @@ def _compose_proc(sd, head, lvl):
     return _conv_to_nk(Wc), bias.reshape(9, 256)
 
 
+# bilinear x2 (align_corners=False) as a 1-D operator: hi-res sample 2j + p + (k - 1), k = conv tap 0..2, is a blend of the
+# low-res samples j-1, j, j+1 with these weights (interior; the two outermost hi-res rows / columns differ and are recomputed
+# by conv1_ring_kernel).  _UP2[p][k][l + 1]
+_UP2 = torch.tensor([[[0.75, 0.25, 0.0], [0.25, 0.75, 0.0], [0.0, 0.75, 0.25]],
+                     [[0.25, 0.75, 0.0], [0.0, 0.75, 0.25], [0.0, 0.25, 0.75]]], dtype=torch.float64)
+
+
+def _compose_up2_conv3(w):
+    """conv3x3(pad 1) o bilinear-x2 == four 3x3 convolutions on the LOW-res grid, one per output phase (py, px):
+    [Cout, Cin, 3, 3] -> [4*Cout, Cin, 3, 3] with row = (py*2 + px)*Cout + o  (persformer_heads decoder: F.interpolate
+    scale_factor=2 followed by conv_fuse_conv1, gravity_head.py:171-173 / latitude_head.py:170-172)."""
+    w = w.double()
+    return torch.cat([torch.einsum("oikm,kl,mn->oiln", w, _UP2[py], _UP2[px]) for py in (0, 1) for px in (0, 1)], 0)
+
+
 def repack(sd, cfg):
     """sd: reference-layout state dict (CPU tensors).  cfg: entry of variants.VARIANTS."""
     out = {}
@@ -118,6 +133,13 @@ def repack(sd, cfg):
     for name, key in (("head.conv0", "conv_fuse_conv0.conv"), ("head.conv1", "conv_fuse_conv1.conv")):
         ks = [f"persformer_heads.{h}.{key}" for h in heads]
         _put_gemm(out, name, torch.stack([_conv_to_nk(sd[k + ".weight"]) for k in ks]), torch.stack([sd[k + ".bias"] for k in ks]).reshape(-1))
+    # conv_fuse_conv1 composed with the x2 upsample in front of it: N = 4 phases x 32 per head on the 160x160 grid; plus the
+    # plain fp32 weights as [head][tap][ci][o] for the border-ring kernel
+    ks = [f"persformer_heads.{h}.conv_fuse_conv1.conv" for h in heads]
+    _put_gemm(out, "head.conv1p", torch.stack([_conv_to_nk(_compose_up2_conv3(sd[k + ".weight"])) for k in ks]),
+              torch.stack([sd[k + ".bias"].repeat(4) for k in ks]).reshape(-1))
+    out["head.conv1f.w"] = torch.stack([sd[k + ".weight"].permute(2, 3, 1, 0).reshape(9, 64, 32) for k in ks]).float().contiguous()
+    out["head.conv1f.b"] = torch.stack([sd[k + ".bias"] for k in ks]).reshape(-1).float().contiguous()
     for short, h, pred in (("g", "gravity_head", "linear_pred_gravity"), ("l", "latitude_head", "linear_pred_latitude")):
         w = sd[f"persformer_heads.{h}.{pred}.weight"]
         out[f"head.pred_{short}.w"] = w.reshape(w.shape[0], 32).float().contiguous()

@@ -179,7 +179,7 @@ def test_kernel_launches_are_counted():
     assert _native.lib().pf_kernel_launch_count() - before > 300
 
 
-@pytest.mark.parametrize("opts", [{"tma": 0}, {"tma": 0, "halo3x3": 0}, {"tma": 0, "tcgen05": 0}, {"attn_mma": 0, "stem_tc": 0}])
+@pytest.mark.parametrize("opts", [{"tma": 0}, {"tma": 0, "halo3x3": 0}, {"tma": 0, "tcgen05": 0}, {"attn_mma": 0, "stem_tc": 0}, {"phase_conv1": 0}])
 def test_legacy_engines_end_to_end(opts):
     """The same forward on the earlier engines (fp32 activations split on the fly): register-staged tcgen05 kernels with
     / without the halo-tile 3x3 variant, and the warp-level HMMA kernel."""
