@@ -75,7 +75,8 @@ def lib():
     if not os.path.exists(LIB_PATH):
         raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                            "(perspectivefields_b200 has no CPU or PyTorch fallback)")
-    L = ctypes.CDLL(LIB_PATH)
+    # PF_B200_LIB: an alternative build of the SAME library (A/B timing of kernel changes on one box: tools/ab.sh)
+    L = ctypes.CDLL(os.environ.get("PF_B200_LIB") or LIB_PATH)
     vp, i32, i64, f32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
     sig = {
         "pf_abi_version": (i32, []),

@@ -22,7 +22,14 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, u
                : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
 }
 
-__global__ void __launch_bounds__(kAmThreads) attention_mma_kernel(const float* __restrict__ q, const float* __restrict__ kv, float* __restrict__ out,
+// SPLIT_IN: q and kv arrive as bf16 hi/lo planes (written by the q / kv GEMM epilogues): K and V are copied into shared memory
+// with cp.async (no conversion work), Q fragments are read as bf16 pairs; the 1/8 scale is applied to S in fp32 (a power of
+// two: identical to scaling q).  Otherwise q, kv are fp32 (operator entry point, legacy graph) and are split on the fly.
+template <bool SPLIT_IN>
+__global__ void __launch_bounds__(kAmThreads) attention_mma_kernel(const float* __restrict__ q, const float* __restrict__ kv,
+                                                                   const __nv_bfloat16* __restrict__ q_hi, const __nv_bfloat16* __restrict__ q_lo,
+                                                                   const __nv_bfloat16* __restrict__ kv_hi, const __nv_bfloat16* __restrict__ kv_lo,
+                                                                   float* __restrict__ out,
                                                                    __nv_bfloat16* __restrict__ shi, __nv_bfloat16* __restrict__ slo, int N, int C,
                                                                    int tiles_per_block) {
   extern __shared__ __align__(128) unsigned char sm_raw[];
@@ -30,8 +37,21 @@ __global__ void __launch_bounds__(kAmThreads) attention_mma_kernel(const float* 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.z, h = blockIdx.y;
   // ---- stage K and V of this (image, head): fp32 -> bf16 hi/lo, [key][64] rows of 128 B, chunk (16 B) index ^= key & 7
-  const float* kvb = kv + (long long)b * kAmKeys * 2 * C + h * kAmD;
-  for (int i = tid; i < kAmKeysPad * (kAmD / 4) * 2; i += kAmThreads) {
+  if (SPLIT_IN) {
+    // 4 planes (K_hi, K_lo, V_hi, V_lo) x 112 keys x 8 chunks of 16 B
+    const long long kvo = (long long)b * kAmKeys * 2 * C + h * kAmD;
+    for (int i = tid; i < 4 * kAmKeysPad * 8; i += kAmThreads) {
+      const int plane = i / (kAmKeysPad * 8), j = i % (kAmKeysPad * 8), key = j >> 3, c = j & 7;
+      const uint32_t dst = sK_hi + plane * kAmPlane + (uint32_t)key * 128u + (uint32_t)((c ^ (key & 7)) << 4);
+      const bool valid = key < kAmKeys;    // keys 100..111: zero fill (src-size 0)
+      const __nv_bfloat16* src = ((plane & 1) ? kv_lo : kv_hi) + kvo + (long long)(valid ? key : 0) * 2 * C + ((plane >> 1) ? C : 0) + c * 8;
+      cp_async16(dst, src, valid);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+  }
+  const float* kvb = SPLIT_IN ? nullptr : kv + (long long)b * kAmKeys * 2 * C + h * kAmD;
+  for (int i = tid; !SPLIT_IN && i < kAmKeysPad * (kAmD / 4) * 2; i += kAmThreads) {
     const int isv = i >= kAmKeysPad * (kAmD / 4);
     const int j = isv ? i - kAmKeysPad * (kAmD / 4) : i;
     const int key = j / (kAmD / 4), d4 = j % (kAmD / 4);
@@ -54,7 +74,17 @@ __global__ void __launch_bounds__(kAmThreads) attention_mma_kernel(const float* 
     const int r0 = q0 + g, r1 = q0 + g + 8;
     // ---- Q fragments (pre-scaled by 1/8, an exact power of two), split into hi / lo
     uint32_t qh[4][4], ql[4][4];
-    {
+    if (SPLIT_IN) {
+      const long long o0 = ((long long)b * N + (r0 < N ? r0 : N - 1)) * C + h * kAmD, o1 = ((long long)b * N + (r1 < N ? r1 : N - 1)) * C + h * kAmD;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const int c0 = ks * 16 + 2 * t;
+        qh[ks][0] = __ldg(reinterpret_cast<const uint32_t*>(q_hi + o0 + c0));     ql[ks][0] = __ldg(reinterpret_cast<const uint32_t*>(q_lo + o0 + c0));
+        qh[ks][1] = __ldg(reinterpret_cast<const uint32_t*>(q_hi + o1 + c0));     ql[ks][1] = __ldg(reinterpret_cast<const uint32_t*>(q_lo + o1 + c0));
+        qh[ks][2] = __ldg(reinterpret_cast<const uint32_t*>(q_hi + o0 + c0 + 8)); ql[ks][2] = __ldg(reinterpret_cast<const uint32_t*>(q_lo + o0 + c0 + 8));
+        qh[ks][3] = __ldg(reinterpret_cast<const uint32_t*>(q_hi + o1 + c0 + 8)); ql[ks][3] = __ldg(reinterpret_cast<const uint32_t*>(q_lo + o1 + c0 + 8));
+      }
+    } else {
       const float* q0p = q + ((long long)b * N + (r0 < N ? r0 : N - 1)) * C + h * kAmD;
       const float* q1p = q + ((long long)b * N + (r1 < N ? r1 : N - 1)) * C + h * kAmD;
 #pragma unroll
@@ -97,6 +127,7 @@ __global__ void __launch_bounds__(kAmThreads) attention_mma_kernel(const float* 
 #pragma unroll
     for (int nt = 0; nt < 14; ++nt) {
       const int k0 = nt * 8 + 2 * t;
+      if (SPLIT_IN) { s[nt][0] *= 0.125f; s[nt][1] *= 0.125f; s[nt][2] *= 0.125f; s[nt][3] *= 0.125f; }
       if (k0 >= kAmKeys) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
       if (k0 + 1 >= kAmKeys) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
       m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
@@ -163,20 +194,25 @@ __global__ void __launch_bounds__(kAmThreads) attention_mma_kernel(const float* 
   }
 }
 
-inline cudaError_t attention_mma_launch(const float* q, const float* kv, float* out, int B, int N, int C, int heads, cudaStream_t st, SplitT sp = SplitT()) {
+// q / kv: fp32 pointers, or (qs / kvs non-empty) split planes with row pitch C / 2C
+inline cudaError_t attention_mma_launch(const float* q, const float* kv, float* out, int B, int N, int C, int heads, cudaStream_t st, SplitT sp = SplitT(),
+                                        SplitT qs = SplitT(), SplitT kvs = SplitT()) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAmSmem);
+    cudaError_t e = cudaFuncSetAttribute(attention_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAmSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAmSmem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
+  if ((qs.hi != nullptr) != (kvs.hi != nullptr) || (qs.hi && (qs.ld != C || kvs.ld != 2 * C))) return cudaErrorInvalidValue;
   const int tiles = cdiv(N, kAmQTile);
   // passes per block: the grid should be about one resident wave (148 SMs x 3 blocks); the K/V staging of a block is
   // amortised over tpb * 64 queries
   int tpb = (tiles * heads * B) / 400;
   tpb = tpb < 1 ? 1 : (tpb > tiles ? tiles : tpb);
   dim3 grid(cdiv(tiles, tpb), heads, B);
-  attention_mma_kernel<<<grid, kAmThreads, kAmSmem, st>>>(q, kv, out, sp.hi, sp.lo, N, C, tpb);
+  if (qs.hi) attention_mma_kernel<true><<<grid, kAmThreads, kAmSmem, st>>>(nullptr, nullptr, qs.hi, qs.lo, kvs.hi, kvs.lo, out, sp.hi, sp.lo, N, C, tpb);
+  else attention_mma_kernel<false><<<grid, kAmThreads, kAmSmem, st>>>(q, kv, nullptr, nullptr, nullptr, nullptr, out, sp.hi, sp.lo, N, C, tpb);
   return cudaGetLastError();
 }
 

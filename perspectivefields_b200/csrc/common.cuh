@@ -66,6 +66,9 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// exact-erf GELU (nn.GELU default; mix_transformers.py:20, convnext.py:52).  libm erff: its small-argument path is a short FMA
+// polynomial; a branch-free Abramowitz-Stegun form (one ex2 + one rcp per value) measured 2x SLOWER in the GEMM epilogue,
+// where the two MUFU operations per element become the bound (profiles/r01_notes.md).
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 __device__ __forceinline__ float warp_sum(float v) {

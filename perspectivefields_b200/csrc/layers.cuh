@@ -227,20 +227,23 @@ inline cudaError_t attention_launch(const float* q, const float* kv, float* out,
 __global__ void __launch_bounds__(256) dwconv3x3_gelu_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C,
                                                              const float* __restrict__ w, const float* __restrict__ bias,
                                                              __nv_bfloat16* __restrict__ shi = nullptr, __nv_bfloat16* __restrict__ slo = nullptr) {
-  // thread = 4 channels x 4 consecutive pixels of one row: 18 activation + 9 weight loads for 4 outputs
-  const int C4 = C >> 2, XG = (W + 3) >> 2;
-  const unsigned total = (unsigned)B * H * XG * C4;      // < 2^31 for every layer of the network: 32-bit index math
+  // thread = 4 channels x (2 rows x 4 consecutive pixels): 24 activation + 9 weight loads (float4) for 8 outputs
+  const int C4 = C >> 2, XG = (W + 3) >> 2, YG = (H + 1) >> 1;
+  const unsigned total = (unsigned)B * YG * XG * C4;      // < 2^31 for every layer of the network: 32-bit index math
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int c4 = (int)(i % (unsigned)C4);
     unsigned r = i / (unsigned)C4;
     const int xg = (int)(r % (unsigned)XG); r /= (unsigned)XG;
-    const int y = (int)(r % (unsigned)H); const int b = (int)(r / (unsigned)H);
+    const int y0 = (int)(r % (unsigned)YG) * 2; const int b = (int)(r / (unsigned)YG);
     const int x0 = xg * 4;
     const float4 bv = __ldg(reinterpret_cast<const float4*>(bias) + c4);
-    float4 acc[4] = {bv, bv, bv, bv};
+    float4 acc[2][4] = {{bv, bv, bv, bv}, {bv, bv, bv, bv}};
+    float4 k[9];
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int iy = y + ky - 1;
+    for (int t = 0; t < 9; ++t) k[t] = __ldg(reinterpret_cast<const float4*>(w + t * C) + c4);
+#pragma unroll
+    for (int ry = 0; ry < 4; ++ry) {          // input rows y0-1 .. y0+2
+      const int iy = y0 + ry - 1;
       if ((unsigned)iy >= (unsigned)H) continue;
       float4 a[6];
 #pragma unroll
@@ -249,22 +252,31 @@ __global__ void __launch_bounds__(256) dwconv3x3_gelu_kernel(const float* __rest
         a[j] = (unsigned)ix < (unsigned)W ? __ldg(reinterpret_cast<const float4*>(in + ((long long)(b * H + iy) * W + ix) * C) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const float4 k = __ldg(reinterpret_cast<const float4*>(w + (ky * 3 + kx) * C) + c4);
+      for (int oy = 0; oy < 2; ++oy) {        // this input row is filter row ky = ry - oy of output row y0 + oy
+        const int ky = ry - oy;
+        if (ky < 0 || ky > 2) continue;
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          acc[p].x = fmaf(a[p + kx].x, k.x, acc[p].x); acc[p].y = fmaf(a[p + kx].y, k.y, acc[p].y);
-          acc[p].z = fmaf(a[p + kx].z, k.z, acc[p].z); acc[p].w = fmaf(a[p + kx].w, k.w, acc[p].w);
+        for (int kx = 0; kx < 3; ++kx) {
+          const float4 kk = k[ky * 3 + kx];
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            acc[oy][p].x = fmaf(a[p + kx].x, kk.x, acc[oy][p].x); acc[oy][p].y = fmaf(a[p + kx].y, kk.y, acc[oy][p].y);
+            acc[oy][p].z = fmaf(a[p + kx].z, kk.z, acc[oy][p].z); acc[oy][p].w = fmaf(a[p + kx].w, kk.w, acc[oy][p].w);
+          }
         }
       }
     }
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
-      if (x0 + p >= W) break;
-      const float4 o = make_float4(gelu_erf(acc[p].x), gelu_erf(acc[p].y), gelu_erf(acc[p].z), gelu_erf(acc[p].w));
-      const long long oi = ((long long)(b * H + y) * W + x0 + p) * C + c4 * 4;
-      if (out) *reinterpret_cast<float4*>(out + oi) = o;
-      if (shi) store_split4(shi, slo, oi, o);
+    for (int oy = 0; oy < 2; ++oy) {
+      if (y0 + oy >= H) break;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        if (x0 + p >= W) break;
+        const float4 o = make_float4(gelu_erf(acc[oy][p].x), gelu_erf(acc[oy][p].y), gelu_erf(acc[oy][p].z), gelu_erf(acc[oy][p].w));
+        const long long oi = ((long long)(b * H + y0 + oy) * W + x0 + p) * C + c4 * 4;
+        if (out) *reinterpret_cast<float4*>(out + oi) = o;
+        if (shi) store_split4(shi, slo, oi, o);
+      }
     }
   }
 }

@@ -114,6 +114,7 @@ struct pf_engine {
   GemmW conv0, conv1;
   GemmW conv1p;                       // conv_fuse_conv1 composed with the x2 upsample in front of it: 4 phases x 32 outputs per head
   const float *conv1f_w, *conv1f_b;   // plain fp32 conv_fuse_conv1 [head][tap][ci][o] / bias, for the border-ring kernel
+  bool use_attn_split = true;         // option "attn_split": q / kv leave their GEMMs as split planes (0 = fp32, split inside the attention kernel)
   bool use_phase = true;              // option "phase_conv1": 0 = materialise the upsampled tensor and run conv1 at 320x320
   const float *pred_g_w, *pred_g_b, *pred_l_w, *pred_l_b;
   const float *pn_stem_w, *pn_stem_b;
@@ -683,7 +684,7 @@ static int run_forward(Fwd& F, const pf_batch* bt, int max_h_for_dry) {
       // x = x + mlp(norm2(x))
       TRY(F.ln(x, t1, rows, C, b.ln2, 1e-6f));
       TRY(F.linear(t1, rows, C, b.fc1, 4 * C, h1));
-      if (!dry) LAUNCHED((dwconv3x3_gelu_kernel<<<ew_grid((long long)n * R * ((R + 3) / 4) * C), 256, 0, st>>>(h1, h2, n, R, R, 4 * C, b.dw_w, b.dw_b), cudaGetLastError()));
+      if (!dry) LAUNCHED((dwconv3x3_gelu_kernel<<<ew_grid((long long)n * ((R + 1) / 2) * ((R + 3) / 4) * C), 256, 0, st>>>(h1, h2, n, R, R, 4 * C, b.dw_w, b.dw_b), cudaGetLastError()));
       TRY(F.linear(h2, rows, 4 * C, b.fc2, C, x, 0, x));
       TRY(F.tapf(x, rows * C, "mit.s%d.b%d", s + 1, i));
     }
@@ -845,11 +846,14 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
     float* x = ar.f(rows * C);
     float* tf = ar.f(rows * C);                      // patch-embed conv output (before its LayerNorm)
     SplitT t1 = F.salloc(rows, C);                   // LayerNorm output (GEMM input only)
-    float* q = ar.f(rows * C);
+    SplitT q = F.salloc(rows, C);                    // q and kv leave their GEMMs as split planes: the attention core's MMA operands
     SplitT a = F.salloc(rows, C);                    // attention output
     float* t2f = ar.f((long long)n * 100 * C);
     SplitT t2 = F.salloc((long long)n * 100, C);
-    float* kv = ar.f((long long)n * 100 * 2 * C);
+    SplitT kv = F.salloc((long long)n * 100, 2 * C);
+    const bool qkv_split = e->use_attn_mma && e->use_attn_split;
+    float* qf = qkv_split ? nullptr : ar.f(rows * C);                        // (fp32 q / kv: CUDA-core attention kernel, or
+    float* kvf = qkv_split ? nullptr : ar.f((long long)n * 100 * 2 * C);     //  option attn_split = 0)
     float* h1 = ar.f(rows * 4 * C);
     SplitT h2 = F.salloc(rows, 4 * C);
     if (s == 0 && e->use_stem_tc) {
@@ -870,21 +874,23 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
     for (int i = 0; i < kMitDepths[s]; ++i) {
       const MitBlockW& b = e->blocks[s][i];
       TRY(F.ln_split(x, t1, rows, C, b.ln1, 1e-6f));
-      { Epi o; o.C = q; o.ldc = C; TRY(F.tgemm(t1, rows, C, 0, b.q, C, o)); }
+      Epi oq, okv;
+      if (qkv_split) { oq.S = q; okv.S = kv; } else { oq.C = qf; oq.ldc = C; okv.C = kvf; okv.ldc = 2 * C; }
+      TRY(F.tgemm(t1, rows, C, 0, b.q, C, oq));
       if (sr > 1) {
         { Epi o; o.C = t2f; o.ldc = C; TRY(F.tconv_gather(t1, n, R, R, C, sr, sr, 0, b.sr, C, o)); }
         TRY(F.ln_split(t2f, t2, (long long)n * 100, C, b.srln, 1e-5f));
-        { Epi o; o.C = kv; o.ldc = 2 * C; TRY(F.tgemm(t2, (long long)n * 100, C, 0, b.kv, 2 * C, o)); }
+        TRY(F.tgemm(t2, (long long)n * 100, C, 0, b.kv, 2 * C, okv));
       } else {
-        Epi o; o.C = kv; o.ldc = 2 * C;
-        TRY(F.tgemm(t1, rows, C, 0, b.kv, 2 * C, o));
+        TRY(F.tgemm(t1, rows, C, 0, b.kv, 2 * C, okv));
       }
-      if (!dry) LAUNCHED(e->use_attn_mma ? attention_mma_launch(q, kv, nullptr, n, N, C, heads, st, a) : attention_launch(q, kv, nullptr, n, N, C, heads, st, a));
+      if (!dry) LAUNCHED(qkv_split ? attention_mma_launch(nullptr, nullptr, nullptr, n, N, C, heads, st, a, q, kv)
+                         : e->use_attn_mma ? attention_mma_launch(qf, kvf, nullptr, n, N, C, heads, st, a) : attention_launch(qf, kvf, nullptr, n, N, C, heads, st, a));
       { Epi o; o.C = x; o.ldc = C; o.res = x; o.ldr = C; TRY(F.tgemm(a, rows, C, 0, b.proj, C, o)); }
       TRY(F.tapf(x, rows * C, "mit.s%d.b%d.attn", s + 1, i));
       TRY(F.ln_split(x, t1, rows, C, b.ln2, 1e-6f));
       { Epi o; o.C = h1; o.ldc = 4 * C; TRY(F.tgemm(t1, rows, C, 0, b.fc1, 4 * C, o)); }
-      if (!dry) LAUNCHED((dwconv3x3_gelu_kernel<<<ew_grid((long long)n * R * ((R + 3) / 4) * C), 256, 0, st>>>(h1, nullptr, n, R, R, 4 * C, b.dw_w, b.dw_b, h2.hi, h2.lo), cudaGetLastError()));
+      if (!dry) LAUNCHED((dwconv3x3_gelu_kernel<<<ew_grid((long long)n * ((R + 1) / 2) * ((R + 3) / 4) * C), 256, 0, st>>>(h1, nullptr, n, R, R, 4 * C, b.dw_w, b.dw_b, h2.hi, h2.lo), cudaGetLastError()));
       { Epi o; o.C = x; o.ldc = C; o.res = x; o.ldr = C; TRY(F.tgemm(h2, rows, 4 * C, 0, b.fc2, C, o)); }
       TRY(F.tapf(x, rows * C, "mit.s%d.b%d", s + 1, i));
     }
@@ -1136,6 +1142,7 @@ int pf_set_option(pf_handle h, const char* name, int value) {
   if (!strcmp(name, "attn_mma")) { h->use_attn_mma = value != 0; return PF_OK; }
   if (!strcmp(name, "stem_tc")) { h->use_stem_tc = value != 0; return PF_OK; }
   if (!strcmp(name, "phase_conv1")) { h->use_phase = value != 0; return PF_OK; }
+  if (!strcmp(name, "attn_split")) { h->use_attn_split = value != 0; return PF_OK; }
   return fail(PF_ERR_ARG, "pf_set_option: unknown option '%s'", name);
 }
 // out[cfg*3 + {0,1,2}] = {milliseconds, algorithmic FLOPs, launches} per GEMM engine configuration (7 configs),
@@ -1264,7 +1271,7 @@ int pf_op_attention_mma(const float* q, const float* kv, float* out, int B, int 
 }
 int pf_op_dwconv3x3_gelu(const float* x, float* y, int B, int H, int W, int C, const float* w, const float* bias, void* stream) {
   if (C % 4) return fail(PF_ERR_ARG, "C %% 4");
-  LAUNCHED((dwconv3x3_gelu_kernel<<<ew_grid((long long)B * H * ((W + 3) / 4) * (C / 4)), 256, 0, (cudaStream_t)stream>>>(x, y, B, H, W, C, w, bias), cudaGetLastError()));
+  LAUNCHED((dwconv3x3_gelu_kernel<<<ew_grid((long long)B * ((H + 1) / 2) * ((W + 3) / 4) * (C / 4)), 256, 0, (cudaStream_t)stream>>>(x, y, B, H, W, C, w, bias), cudaGetLastError()));
   return PF_OK;
 }
 int pf_op_dwconv7x7(const float* x, float* y, int B, int H, int W, int C, const float* w, const float* bias, void* stream) {
