@@ -63,10 +63,11 @@ template <int BN, int MODE, int KB> struct TmaCfg {
   static constexpr int kAPlane = 128 * KB * 2;                  // MODE_GEMM: plane of a 128 x KB A tile
   static constexpr int kStage = (MODE == MODE_GEMM ? 2 * kAPlane : 0) + 2 * kBPlane;
   static constexpr int kABuf = 2 * kHtPlaneBytes;               // MODE_HALO: hi + lo halo planes (1024 B multiples)
-  // MODE_GEMM epilogue staging: per epilogue warp 2 x 4 KB output tiles (32 rows x 32 columns fp32, or bf16 hi + lo) for the
-  // TMA stores and 2 x 4 KB residual tiles filled by TMA loads; plus bias / layer-scale copies (2 x BN floats per warp).
+  // MODE_GEMM epilogue staging, 64 KB.  With a residual input: warps 4-7, each 2 x 4 KB output tiles (32 rows x 32 columns fp32,
+  // or bf16 hi + lo) for the TMA stores and 2 x 4 KB residual tiles filled by TMA loads.  Without one: warps 4-11 (two per TMEM
+  // lane quarter, alternate 32-column chunks), each 2 x 4 KB output tiles.  Plus bias / layer-scale copies (2 x 256 floats per warp).
   static constexpr int kEpiStage = MODE == MODE_GEMM ? 4 * 16384 : 0;
-  static constexpr int kEpiVec = MODE == MODE_GEMM ? 4 * 2 * 256 * 4 : 0;
+  static constexpr int kEpiVec = MODE == MODE_GEMM ? 8 * 2 * 256 * 4 : 0;
   static constexpr int kBudget = 225 * 1024 - kEpiStage - kEpiVec - (MODE == MODE_HALO ? 2 * kABuf : 0);
   static constexpr int kStagesRaw = kBudget / kStage;
   static constexpr int kStages = kStagesRaw > 16 ? 16 : kStagesRaw;
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.a_hi); tma_prefetch_desc(&maps.a_lo); tma_prefetch_desc(&maps.b_hi); tma_prefetch_desc(&maps.b_lo);
     for (int s = 0; s < NS; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(full_a(i), 1); mbar_init(empty_a(i), 1); mbar_init(tmem_full(i), 1); mbar_init(tmem_empty(i), MODE == MODE_GEMM ? 128 : 256); }
+    for (int i = 0; i < 2; ++i) { mbar_init(full_a(i), 1); mbar_init(empty_a(i), 1); mbar_init(tmem_full(i), 1); mbar_init(tmem_empty(i), (MODE == MODE_GEMM && p.res) ? 128 : 256); }
     for (int i = 0; i < 8; ++i) mbar_init(res_bar(i >> 1, i & 1), 1);
     fence_mbar_init();
   }
@@ -279,13 +280,16 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
     // Per warp (32 tile rows) and 32-column chunk: TMEM -> registers, + bias, activation, layer scale, + residual tile (TMA-
     // loaded into swizzled smem one chunk ahead), then the result goes to a swizzled smem tile and ONE thread issues a
     // bulk-tensor store: global traffic is full 128 B rows written by the copy engine instead of 16 B-per-row thread stores.
-    if (warp < 8) {
+    const bool has_res = p.res != nullptr;
+    if (warp < 8 || !has_res) {
       const int q = warp & 3;
-      const uint32_t stg = epi_base + q * 16384;            // out[2] at +0, +4096 ; res[2] at +8192, +12288
+      const int ew = warp - 4;                              // 0..7
+      const int ch0 = has_res ? 0 : (ew >> 2), chs = has_res ? 1 : 2;   // this warp's 32-column chunks: ch0, ch0 + chs, ...
+      // residual launches: out[2] at +0, +4096 ; res[2] at +8192, +12288 (per quarter); others: out[2] per warp
+      const uint32_t stg = has_res ? epi_base + q * 16384 : epi_base + ew * 8192;
       unsigned char* stg_p = sm + (stg - sbase);
-      float* bias_s = reinterpret_cast<float*>(sm + (vec_base - sbase)) + q * 512;
+      float* bias_s = reinterpret_cast<float*>(sm + (vec_base - sbase)) + ew * 512;
       float* gamma_s = bias_s + 256;
-      const bool has_res = p.res != nullptr;
       uint32_t rl = 0, rc = 0;                              // residual tiles requested / consumed by this warp
       uint32_t oc = 0;                                      // output tiles staged so far (buffer = oc & 1, across tiles)
       int tl = 0;
@@ -312,7 +316,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
         mbar_wait(tmem_full(as), (tl >> 1) & 1);
         tc_fence_after();
 #pragma unroll 1
-        for (int ch = 0; ch < nch; ++ch) {
+        for (int ch = ch0; ch < nch; ch += chs) {
           uint32_t v[32];
           tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + ch * 32), v);
           if (!warp_active) continue;                                  // whole warp beyond the matrix (warp-uniform)
