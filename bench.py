@@ -157,6 +157,14 @@ def run_reference(args, rank):
     }), flush=True)
 
 
+def _has_symbol(L, name):
+    try:
+        getattr(L, name)
+        return True
+    except AttributeError:
+        return False
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -228,8 +236,6 @@ def main():
         h0 = time.perf_counter()
         out = eng.forward(B, heights, widths, blob=blob, offsets=offsets)
         host_fwd += time.perf_counter() - h0
-        if _ == args.steps - 2 and args.steps >= 4:
-            sampler.sample()   # one sample with the launch queue full (the host has been throttled to the GPU's pace by now)
         if tracing:
             step_host.append(round((time.perf_counter() - h0) * 1000, 2))
             ev = torch.cuda.Event(enable_timing=True)
@@ -265,6 +271,29 @@ def main():
     prof = (ctypes.c_double * 21)()
     _native.check(L.pf_profile_read(eng.handle, prof))
     _native.check(L.pf_profile_enable(eng.handle, 0))
+    # per-kernel pass: the same K steps with a CUDA-event pair around EVERY launch (in-pipeline time of each kernel, warm L2,
+    # real neighbours -- unlike ncu's serialised cold-cache replay); the events cost a few percent, hence a pass of its own
+    per_kernel = {}
+    have_kp = _has_symbol(L, "pf_profile_kernels_read")   # (an older library under A/B test may predate it)
+    if have_kp:
+        _native.check(L.pf_profile_kernels_enable(eng.handle, 700 * args.steps))
+    barrier()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(args.steps):
+        flush.fill_(1)
+        eng.forward(B, heights, widths, blob=blob, offsets=offsets)
+    k1.record()
+    barrier()
+    buf = ctypes.create_string_buffer(1 << 16)
+    nbytes = 0
+    if have_kp:
+        nbytes = _native.check(L.pf_profile_kernels_read(eng.handle, buf, len(buf)))
+        _native.check(L.pf_profile_kernels_enable(eng.handle, 0))
+    for line in buf.raw[:nbytes].decode().splitlines()[1:]:
+        name, cnt, kms = line.rsplit(",", 2)
+        per_kernel[name] = {"ms_per_step": round(float(kms) / args.steps, 4), "launches_per_step": int(cnt) / args.steps}
+    per_kernel["_pass_ms_per_step"] = round(k0.elapsed_time(k1) / args.steps, 3)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -295,12 +324,14 @@ def main():
             for i, d in enumerate(r):
                 for k in keys:
                     bufs[k][i].copy_(d[k], non_blocking=True)
-                    d[k].record_stream(copy_stream)
         if len(pending) >= 2:
-            pending.pop(0).synchronize()    # the buffers about to be reused have been filled
+            old_ev, old_r = pending.pop(0)
+            old_ev.synchronize()            # the buffers about to be reused have been filled ...
+            del old_r                       # ... and only now are that step's device results released (no record_stream: the
+                                            # caching allocator then recycles the same blocks every step instead of growing)
         ev = torch.cuda.Event()
         ev.record(copy_stream)
-        pending.append(ev)
+        pending.append((ev, r))
 
     for _ in range(max(args.warmup, 1)):
         e2e_step()
@@ -388,6 +419,7 @@ def main():
             "gpu_launches": int(launches),
             "host_enqueue_ms_per_step": host_enqueue_ms, "host_pf_forward_ms_per_step": host_fwd * 1000 / args.steps,
             "roofline": roofline,
+            "per_kernel": per_kernel,
             "cpu_baseline": cpu,
         }), flush=True)
     if world > 1:

@@ -97,6 +97,11 @@ int pf_forward(pf_handle h, const pf_batch* batch, void* workspace, int64_t work
  *  5: TMA+tcgen05 GEMM, 6: TMA+tcgen05 halo 3x3) accumulated since the previous read; synchronise the stream first. */
 int pf_profile_enable(pf_handle h, int on /* 0 off, 1 on, n > 1: on + pre-create events for n GEMM launches */);
 int pf_profile_read(pf_handle h, double* out21);
+/* A CUDA-event pair around EVERY kernel launch of the forward graph: in-pipeline time per kernel (bench.py "per_kernel").
+ * enable(max_launches > 0) pre-creates the events and starts recording, enable(0) stops.  read() writes a text table
+ * "kernel,launches,ms\n..." (aggregated since the last read) into buf and returns its length; synchronise the stream first. */
+int pf_profile_kernels_enable(pf_handle h, int max_launches);
+int pf_profile_kernels_read(pf_handle h, char* buf, int cap);
 
 /* Engine options.  "tma" (default 1): the forward graph runs on the persistent TMA -> tcgen05 -> TMEM engine with pre-split
  * bf16 hi/lo activations (gemm_tma.cuh).  With "tma" = 0 the earlier engines are used (fp32 activations split on the fly):

@@ -90,6 +90,8 @@ def lib():
         "pf_forward": (i32, [vp, ctypes.POINTER(pf_batch), vp, i64, vp]),
         "pf_profile_enable": (i32, [vp, i32]),
         "pf_profile_read": (i32, [vp, ctypes.POINTER(ctypes.c_double)]),
+        "pf_profile_kernels_enable": (i32, [vp, i32]),
+        "pf_profile_kernels_read": (i32, [vp, ctypes.c_char_p, i32]),
         "pf_debug_enable": (i32, [vp, i32]),
         "pf_debug_count": (i32, [vp]),
         "pf_debug_name": (ctypes.c_char_p, [vp, i32]),
@@ -106,7 +108,12 @@ def lib():
         "pf_op_preprocess": (i32, [vp, i32, i32, ctypes.POINTER(f32), ctypes.POINTER(f32), vp, vp]),
     }
     for name, (res, args) in sig.items():
-        fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
+        try:
+            fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
+        except AttributeError:
+            if os.environ.get("PF_B200_LIB"):   # an older build under A/B test may predate an entry point
+                continue
+            raise
         fn.restype, fn.argtypes = res, args
     if L.pf_abi_version() != 1:
         raise RuntimeError("libpf_b200.so ABI version mismatch")
@@ -115,7 +122,7 @@ def lib():
 
 
 EXPORTS = ["pf_abi_version", "pf_last_error", "pf_kernel_launch_count", "pf_create", "pf_destroy", "pf_set_weight",
-           "pf_finalize", "pf_workspace_bytes", "pf_forward", "pf_profile_enable", "pf_profile_read", "pf_set_option", "pf_debug_enable", "pf_debug_count", "pf_debug_name",
+           "pf_finalize", "pf_workspace_bytes", "pf_forward", "pf_profile_enable", "pf_profile_read", "pf_profile_kernels_enable", "pf_profile_kernels_read", "pf_set_option", "pf_debug_enable", "pf_debug_count", "pf_debug_name",
            "pf_debug_numel", "pf_debug_copy", "pf_op_conv_gemm", "pf_op_layernorm", "pf_op_attention", "pf_op_attention_mma",
            "pf_op_dwconv3x3_gelu", "pf_op_dwconv7x7", "pf_op_upsample2x", "pf_op_preprocess"]
 

@@ -63,9 +63,9 @@ template <int BN, int MODE, int KB> struct TmaCfg {
   static constexpr int kAPlane = 128 * KB * 2;                  // MODE_GEMM: plane of a 128 x KB A tile
   static constexpr int kStage = (MODE == MODE_GEMM ? 2 * kAPlane : 0) + 2 * kBPlane;
   static constexpr int kABuf = 2 * kHtPlaneBytes;               // MODE_HALO: hi + lo halo planes (1024 B multiples)
-  // MODE_GEMM epilogue staging, 64 KB.  With a residual input: warps 4-7, each 2 x 4 KB output tiles (32 rows x 32 columns fp32,
-  // or bf16 hi + lo) for the TMA stores and 2 x 4 KB residual tiles filled by TMA loads.  Without one: warps 4-11 (two per TMEM
-  // lane quarter, alternate 32-column chunks), each 2 x 4 KB output tiles.  Plus bias / layer-scale copies (2 x 256 floats per warp).
+  // MODE_GEMM epilogue staging, 64 KB: warps 4-11 (two per TMEM lane quarter, alternate 32-column chunks), each two 4 KB tiles
+  // (32 rows x 32 columns fp32, or bf16 hi + lo) that receive the residual tile (TMA load) and send the result (TMA store).
+  // Plus bias / layer-scale copies (2 x 256 floats per warp).
   static constexpr int kEpiStage = MODE == MODE_GEMM ? 4 * 16384 : 0;
   static constexpr int kEpiVec = MODE == MODE_GEMM ? 8 * 2 * 256 * 4 : 0;
   static constexpr int kBudget = 225 * 1024 - kEpiStage - kEpiVec - (MODE == MODE_HALO ? 2 * kABuf : 0);
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
   auto tmem_full = [&](int i) { return bars + 8u * (2 * NS + 4 + i); };
   auto tmem_empty = [&](int i) { return bars + 8u * (2 * NS + 6 + i); };
   const uint32_t tmem_slot = bars + 8u * (2 * NS + 8);
-  auto res_bar = [&](int q, int i) { return bars + 8u * (2 * NS + 9 + 2 * q + i); };   // MODE_GEMM: residual tiles landed
+  auto res_bar = [&](int w, int i) { return bars + 8u * (2 * NS + 9 + 2 * w + i); };   // MODE_GEMM: residual tile i of epilogue warp w landed
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_tiles = cdiv(p.N, BN);
@@ -152,8 +152,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.a_hi); tma_prefetch_desc(&maps.a_lo); tma_prefetch_desc(&maps.b_hi); tma_prefetch_desc(&maps.b_lo);
     for (int s = 0; s < NS; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(full_a(i), 1); mbar_init(empty_a(i), 1); mbar_init(tmem_full(i), 1); mbar_init(tmem_empty(i), (MODE == MODE_GEMM && p.res) ? 128 : 256); }
-    for (int i = 0; i < 8; ++i) mbar_init(res_bar(i >> 1, i & 1), 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(full_a(i), 1); mbar_init(empty_a(i), 1); mbar_init(tmem_full(i), 1); mbar_init(tmem_empty(i), 256); }
+    for (int i = 0; i < 16; ++i) mbar_init(res_bar(i >> 1, i & 1), 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
@@ -276,22 +276,24 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
       }
     }
   } else if (MODE == MODE_GEMM && warp >= 4) {
-    // ======================================================================= MODE_GEMM epilogue: warps 4-7, TMA stores
+    // ======================================================================= MODE_GEMM epilogue: warps 4-11, TMA loads / stores
     // Per warp (32 tile rows) and 32-column chunk: TMEM -> registers, + bias, activation, layer scale, + residual tile (TMA-
     // loaded into swizzled smem one chunk ahead), then the result goes to a swizzled smem tile and ONE thread issues a
     // bulk-tensor store: global traffic is full 128 B rows written by the copy engine instead of 16 B-per-row thread stores.
-    const bool has_res = p.res != nullptr;
-    if (warp < 8 || !has_res) {
+    // Eight warps: TMEM lane quarter q = warp % 4, warps w and w + 4 take alternate 32-column chunks.  Each warp owns two 4 KB
+    // smem tiles used in turn: the residual tile of a chunk is TMA-loaded INTO the tile, the result overwrites it in place (a lane
+    // reads and writes only its own row) and is TMA-stored from it.  The residual of the warp's next chunk is requested as soon
+    // as the store that last used the other tile has been read out.
+    {
+      const bool has_res = p.res != nullptr;
       const int q = warp & 3;
       const int ew = warp - 4;                              // 0..7
-      const int ch0 = has_res ? 0 : (ew >> 2), chs = has_res ? 1 : 2;   // this warp's 32-column chunks: ch0, ch0 + chs, ...
-      // residual launches: out[2] at +0, +4096 ; res[2] at +8192, +12288 (per quarter); others: out[2] per warp
-      const uint32_t stg = has_res ? epi_base + q * 16384 : epi_base + ew * 8192;
+      const int ch0 = ew >> 2;                              // this warp's chunks: ch0, ch0 + 2, ...
+      const uint32_t stg = epi_base + ew * 8192;
       unsigned char* stg_p = sm + (stg - sbase);
       float* bias_s = reinterpret_cast<float*>(sm + (vec_base - sbase)) + ew * 512;
       float* gamma_s = bias_s + 256;
-      uint32_t rl = 0, rc = 0;                              // residual tiles requested / consumed by this warp
-      uint32_t oc = 0;                                      // output tiles staged so far (buffer = oc & 1, across tiles)
+      uint32_t cc = 0;                                      // chunks staged so far by this warp (tile = cc & 1, barrier phase = (cc >> 1) & 1)
       int tl = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
         int mt, g, n0;
@@ -305,31 +307,31 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
           gamma_s[j] = (p.gamma && ok) ? __ldg(p.gamma + n0 + j) : 1.f;
         }
         __syncwarp();
-        const bool warp_active = row0 < p.M && nch > 0;      // warp-uniform: this warp's 32 rows intersect the matrix
-        if (has_res && warp_active) {
-          if (lane == 0) {
-            mbar_expect_tx(res_bar(q, rl & 1), 4096);
-            tma_load_2d(stg + 8192 + (rl & 1) * 4096, &maps.res, res_bar(q, rl & 1), p.r_coff + n0, row0);
-          }
-          ++rl;
+        const bool warp_active = row0 < p.M && ch0 < nch;    // warp-uniform: this warp's rows / chunks intersect the matrix
+        if (has_res && warp_active && lane == 0) {          // residual of this tile's first chunk
+          bulk_wait_read<0>();                              // (both tiles free: every earlier store has been read out)
+          mbar_expect_tx(res_bar(ew, cc & 1), 4096);
+          tma_load_2d(stg + (cc & 1) * 4096, &maps.res, res_bar(ew, cc & 1), p.r_coff + n0 + ch0 * 32, row0);
         }
         mbar_wait(tmem_full(as), (tl >> 1) & 1);
         tc_fence_after();
 #pragma unroll 1
-        for (int ch = ch0; ch < nch; ch += chs) {
+        for (int ch = ch0; ch < nch; ch += 2) {
           uint32_t v[32];
           tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + ch * 32), v);
           if (!warp_active) continue;                                  // whole warp beyond the matrix (warp-uniform)
-          const int ob = oc & 1;
-          ++oc;
-          if (has_res && ch + 1 < nch) {                               // residual tile of the next chunk
-            if (lane == 0) {
-              mbar_expect_tx(res_bar(q, rl & 1), 4096);
-              tma_load_2d(stg + 8192 + (rl & 1) * 4096, &maps.res, res_bar(q, rl & 1), p.r_coff + n0 + (ch + 1) * 32, row0);
+          const int ob = cc & 1;
+          if (lane == 0) {
+            if (has_res) {
+              bulk_wait_read<0>();                                     // the store of the previous chunk has read tile ob ^ 1
+              if (ch + 2 < nch) {                                      // residual of the next chunk into it
+                mbar_expect_tx(res_bar(ew, ob ^ 1), 4096);
+                tma_load_2d(stg + (ob ^ 1) * 4096, &maps.res, res_bar(ew, ob ^ 1), p.r_coff + n0 + (ch + 2) * 32, row0);
+              }
+            } else {
+              bulk_wait_read<1>();                                     // the store that used tile ob two chunks ago has read it
             }
-            ++rl;
           }
-          if (lane == 0) bulk_wait_read<1>();                          // the store that used out[ob] two chunks ago has read it
           __syncwarp();
           float o[32];
 #pragma unroll
@@ -352,18 +354,19 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
               o[j] *= gv.x; o[j + 1] *= gv.y; o[j + 2] *= gv.z; o[j + 3] *= gv.w;
             }
           }
+          unsigned char* ob_p = stg_p + ob * 4096;
           if (has_res) {
-            mbar_wait(res_bar(q, rc & 1), (rc >> 1) & 1);
-            const unsigned char* rb = stg_p + 8192 + (rc & 1) * 4096 + lane * 128;
+            mbar_wait(res_bar(ew, ob), (cc >> 1) & 1);
+            const unsigned char* rb = ob_p + lane * 128;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               float4 rv = *reinterpret_cast<const float4*>(rb + ((j ^ (lane & 7)) << 4));
               if (p.res_relu) { rv.x = fmaxf(rv.x, 0.f); rv.y = fmaxf(rv.y, 0.f); rv.z = fmaxf(rv.z, 0.f); rv.w = fmaxf(rv.w, 0.f); }
               o[4 * j] += rv.x; o[4 * j + 1] += rv.y; o[4 * j + 2] += rv.z; o[4 * j + 3] += rv.w;
             }
-            ++rc;
+            __syncwarp();      // (split output: a lane's 64 B hi/lo rows overlap other lanes' 128 B residual rows)
           }
-          unsigned char* ob_p = stg_p + ob * 4096;
+          ++cc;
           if (p.C) {
 #pragma unroll
             for (int j = 0; j < 8; ++j)

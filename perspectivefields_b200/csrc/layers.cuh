@@ -282,42 +282,57 @@ __global__ void __launch_bounds__(256) dwconv3x3_gelu_kernel(const float* __rest
 }
 
 // Depthwise 7x7 conv (pad 3) + bias on NHWC -- ConvNeXt block head, convnext.py:28-30,48.  w: [49][C].
-// thread = 4 channels x 4 consecutive pixels of one row: per filter row 10 activation + 7 weight loads for 28 tap-pixels.
+// thread = 4 channels x (2 rows x 8 consecutive pixels): per input row 14 activation loads serve both output rows; 98 weight +
+// 112 activation loads (16 B) for 3136 FMAs, which balances the L1 path against the FMA pipe (one row x 4 pixels was L1-bound 2.4x)
 __global__ void __launch_bounds__(256) dwconv7x7_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C,
                                                         const float* __restrict__ w, const float* __restrict__ bias) {
-  const int C4 = C >> 2, XG = (W + 3) >> 2;
-  const unsigned total = (unsigned)B * H * XG * C4;
+  const int C4 = C >> 2, XG = (W + 7) >> 3, YG = (H + 1) >> 1;
+  const unsigned total = (unsigned)B * YG * XG * C4;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int c4 = (int)(i % (unsigned)C4);
     unsigned r = i / (unsigned)C4;
     const int xg = (int)(r % (unsigned)XG); r /= (unsigned)XG;
-    const int y = (int)(r % (unsigned)H); const int b = (int)(r / (unsigned)H);
-    const int x0 = xg * 4;
+    const int y0 = (int)(r % (unsigned)YG) * 2; const int b = (int)(r / (unsigned)YG);
+    const int x0 = xg * 8;
     const float4 bv = __ldg(reinterpret_cast<const float4*>(bias) + c4);
-    float4 acc[4] = {bv, bv, bv, bv};
-    for (int ky = 0; ky < 7; ++ky) {
-      const int iy = y + ky - 3;
-      if ((unsigned)iy >= (unsigned)H) continue;
-      float4 a[10];
+    float4 acc[2][8];
 #pragma unroll
-      for (int j = 0; j < 10; ++j) {
+    for (int oy = 0; oy < 2; ++oy)
+#pragma unroll
+      for (int p = 0; p < 8; ++p) acc[oy][p] = bv;
+#pragma unroll
+    for (int ry = 0; ry < 8; ++ry) {          // input rows y0-3 .. y0+4
+      const int iy = y0 + ry - 3;
+      if ((unsigned)iy >= (unsigned)H) continue;
+      float4 a[14];
+#pragma unroll
+      for (int j = 0; j < 14; ++j) {
         const int ix = x0 - 3 + j;
         a[j] = (unsigned)ix < (unsigned)W ? __ldg(reinterpret_cast<const float4*>(in + ((long long)(b * H + iy) * W + ix) * C) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
-      for (int kx = 0; kx < 7; ++kx) {
-        const float4 k = __ldg(reinterpret_cast<const float4*>(w + (ky * 7 + kx) * C) + c4);
+      for (int oy = 0; oy < 2; ++oy) {        // this input row is filter row ky = ry - oy of output row y0 + oy
+        const int ky = ry - oy;
+        if (ky < 0 || ky > 6) continue;
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          acc[p].x = fmaf(a[p + kx].x, k.x, acc[p].x); acc[p].y = fmaf(a[p + kx].y, k.y, acc[p].y);
-          acc[p].z = fmaf(a[p + kx].z, k.z, acc[p].z); acc[p].w = fmaf(a[p + kx].w, k.w, acc[p].w);
+        for (int kx = 0; kx < 7; ++kx) {
+          const float4 k = __ldg(reinterpret_cast<const float4*>(w + (ky * 7 + kx) * C) + c4);
+#pragma unroll
+          for (int p = 0; p < 8; ++p) {
+            acc[oy][p].x = fmaf(a[p + kx].x, k.x, acc[oy][p].x); acc[oy][p].y = fmaf(a[p + kx].y, k.y, acc[oy][p].y);
+            acc[oy][p].z = fmaf(a[p + kx].z, k.z, acc[oy][p].z); acc[oy][p].w = fmaf(a[p + kx].w, k.w, acc[oy][p].w);
+          }
         }
       }
     }
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
-      if (x0 + p >= W) break;
-      *reinterpret_cast<float4*>(out + ((long long)(b * H + y) * W + x0 + p) * C + c4 * 4) = acc[p];
+    for (int oy = 0; oy < 2; ++oy) {
+      if (y0 + oy >= H) break;
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        if (x0 + p >= W) break;
+        *reinterpret_cast<float4*>(out + ((long long)(b * H + y0 + oy) * W + x0 + p) * C + c4 * 4) = acc[oy][p];
+      }
     }
   }
 }

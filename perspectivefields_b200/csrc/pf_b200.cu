@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <cctype>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -53,10 +54,28 @@ static bool sync_debug() {
   if (v < 0) v = getenv("PF_SYNC_DEBUG") ? 1 : 0;
   return v == 1;
 }
+// pf_profile_kernels_*: a CUDA-event pair around EVERY launch of the forward graph (in-pipeline time per kernel, bench.py's
+// "per_kernel" table).  Off by default: the event records cost a few percent, so bench.py uses a separate pass for it.
+struct KernelProf {
+  bool on = false;
+  cudaStream_t st = nullptr;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  struct Rec { const char* expr; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  cudaEvent_t next() { return used < pool.size() ? pool[used++] : nullptr; }
+};
+static KernelProf g_kp;
 #define LAUNCHED(expr)                                                                              \
   do {                                                                                              \
+    cudaEvent_t ka__ = g_kp.on ? g_kp.next() : nullptr;                                             \
+    if (ka__) cudaEventRecord(ka__, g_kp.st);                                                       \
     cudaError_t e__ = (expr);                                                                       \
     g_launches.fetch_add(1, std::memory_order_relaxed);                                             \
+    if (ka__) {                                                                                     \
+      cudaEvent_t kb__ = g_kp.next();                                                               \
+      if (kb__) { cudaEventRecord(kb__, g_kp.st); g_kp.recs.push_back({#expr, ka__, kb__}); }       \
+    }                                                                                               \
     if (e__ == cudaSuccess && sync_debug()) e__ = cudaDeviceSynchronize();                          \
     if (e__ != cudaSuccess) return fail(PF_ERR_CUDA, "%s: %s (%s:%d, after tap '%s')", #expr, cudaGetErrorString(e__), __FILE__, __LINE__, g_crumb); \
   } while (0)
@@ -362,6 +381,13 @@ struct Fwd {
     e->taps.push_back({name, {cp, numel}});
     return PF_OK;
   }
+  // (two names so that the per-kernel profile separates the GEMM-mode and halo-mode launches)
+  static cudaError_t gemm_tma_gemm_mode(const TmaMaps& maps, const TmaGemmParams& p, int bn, int kb, int sms, cudaStream_t st, const PredTail* pred) {
+    return gemm_tma_launch(MODE_GEMM, maps, p, bn, kb, sms, st, pred);
+  }
+  static cudaError_t gemm_tma_halo_mode(const TmaMaps& maps, const TmaGemmParams& p, int bn, int kb, int sms, cudaStream_t st, const PredTail* pred) {
+    return gemm_tma_launch(MODE_HALO, maps, p, bn, kb, sms, st, pred);
+  }
   int launch_tma(int mode, const TmaMaps& maps, const TmaGemmParams& p, const PredTail* pred = nullptr) {
     const int bn = tma_pick_bn(p.N, mode), kb = tma_pick_kb(bn, p.K, mode);
     if (e->profile) {
@@ -375,12 +401,14 @@ struct Fwd {
       r.cfg = mode == MODE_GEMM ? 5 : 6;
       r.M = (int)Mrows; r.N = p.N; r.K = p.K; r.KH = mode == MODE_GEMM ? 1 : 3; r.stride = 1; r.groups = p.groups; r.Cin = p.Cin;
       CU(cudaEventRecord(r.a, st));
-      LAUNCHED(gemm_tma_launch(mode, maps, p, bn, kb, e->sm_count, st, pred));
+      if (mode == MODE_GEMM) LAUNCHED(gemm_tma_gemm_mode(maps, p, bn, kb, e->sm_count, st, pred));
+      else LAUNCHED(gemm_tma_halo_mode(maps, p, bn, kb, e->sm_count, st, pred));
       CU(cudaEventRecord(r.b, st));
       e->prof.push_back(r);
       return PF_OK;
     }
-    LAUNCHED(gemm_tma_launch(mode, maps, p, bn, kb, e->sm_count, st, pred));
+    if (mode == MODE_GEMM) LAUNCHED(gemm_tma_gemm_mode(maps, p, bn, kb, e->sm_count, st, pred));
+    else LAUNCHED(gemm_tma_halo_mode(maps, p, bn, kb, e->sm_count, st, pred));
     return PF_OK;
   }
   struct Epi {   // epilogue options of one TMA GEMM / conv
@@ -789,7 +817,7 @@ static int run_forward(Fwd& F, const pf_batch* bt, int max_h_for_dry) {
       float* h = ar.f(rows * 4 * C);
       for (int j = 0; j < kCnxDepths[s]; ++j) {
         const CnxBlockW& b = e->pn_blocks[s][j];
-        if (!dry) LAUNCHED((dwconv7x7_kernel<<<ew_grid((long long)n * r * ((r + 3) / 4) * (C / 4)), 256, 0, st>>>(x, y, n, r, r, C, b.dw_w, b.dw_b), cudaGetLastError()));
+        if (!dry) LAUNCHED((dwconv7x7_kernel<<<ew_grid((long long)n * ((r + 1) / 2) * ((r + 7) / 8) * (C / 4)), 256, 0, st>>>(x, y, n, r, r, C, b.dw_w, b.dw_b), cudaGetLastError()));
         TRY(F.ln(y, y, rows, C, b.ln, 1e-6f));
         TRY(F.linear(y, rows, C, b.pw1, 4 * C, h, 2));
         TRY(F.linear(h, rows, 4 * C, b.pw2, C, x, 0, x, b.gamma));
@@ -884,8 +912,11 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
       } else {
         TRY(F.tgemm(t1, rows, C, 0, b.kv, 2 * C, okv));
       }
-      if (!dry) LAUNCHED(qkv_split ? attention_mma_launch(nullptr, nullptr, nullptr, n, N, C, heads, st, a, q, kv)
-                         : e->use_attn_mma ? attention_mma_launch(qf, kvf, nullptr, n, N, C, heads, st, a) : attention_launch(qf, kvf, nullptr, n, N, C, heads, st, a));
+      if (!dry) {
+        if (qkv_split) LAUNCHED(attention_mma_launch(nullptr, nullptr, nullptr, n, N, C, heads, st, a, q, kv));
+        else if (e->use_attn_mma) LAUNCHED(attention_mma_launch(qf, kvf, nullptr, n, N, C, heads, st, a));
+        else LAUNCHED(attention_launch(qf, kvf, nullptr, n, N, C, heads, st, a));
+      }
       { Epi o; o.C = x; o.ldc = C; o.res = x; o.ldr = C; TRY(F.tgemm(a, rows, C, 0, b.proj, C, o)); }
       TRY(F.tapf(x, rows * C, "mit.s%d.b%d.attn", s + 1, i));
       TRY(F.ln_split(x, t1, rows, C, b.ln2, 1e-6f));
@@ -1019,7 +1050,7 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
       SplitT h = F.salloc(rows, 4 * C);
       for (int j = 0; j < kCnxDepths[s]; ++j) {
         const CnxBlockW& b = e->pn_blocks[s][j];
-        if (!dry) LAUNCHED((dwconv7x7_kernel<<<ew_grid((long long)n * r * ((r + 3) / 4) * (C / 4)), 256, 0, st>>>(x, yf, n, r, r, C, b.dw_w, b.dw_b), cudaGetLastError()));
+        if (!dry) LAUNCHED((dwconv7x7_kernel<<<ew_grid((long long)n * ((r + 1) / 2) * ((r + 7) / 8) * (C / 4)), 256, 0, st>>>(x, yf, n, r, r, C, b.dw_w, b.dw_b), cudaGetLastError()));
         TRY(F.ln_split(yf, y, rows, C, b.ln, 1e-6f));
         { Epi o; o.S = h; o.act = 2; TRY(F.tgemm(y, rows, C, 0, b.pw1, 4 * C, o)); }
         { Epi o; o.C = x; o.ldc = C; o.res = x; o.ldr = C; o.gamma = b.gamma; TRY(F.tgemm(h, rows, 4 * C, 0, b.pw2, C, o)); }
@@ -1120,6 +1151,7 @@ int pf_forward(pf_handle h, const pf_batch* bt, void* workspace, int64_t workspa
   }
   if (((uintptr_t)workspace & 255) != 0) return fail(PF_ERR_ARG, "pf_forward: workspace must be 256-byte aligned");
   h->taps.clear();
+  g_kp.st = (cudaStream_t)stream;
   return h->use_tma ? run_forward_tma(F, bt) : run_forward(F, bt, 0);
 }
 
@@ -1133,6 +1165,52 @@ int pf_profile_enable(pf_handle h, int on) {
     h->ev_pool.push_back(ev);
   }
   return PF_OK;
+}
+int pf_profile_kernels_enable(pf_handle h, int max_launches) {
+  if (!h) return fail(PF_ERR_ARG, "null handle");
+  CU(cudaSetDevice(h->device));
+  g_kp.on = max_launches > 0;
+  g_kp.used = 0;
+  g_kp.recs.clear();
+  while ((long long)g_kp.pool.size() < 2LL * max_launches) {
+    cudaEvent_t ev;
+    CU(cudaEventCreate(&ev));
+    g_kp.pool.push_back(ev);
+  }
+  return PF_OK;
+}
+// text table "kernel,launches,ms\n" aggregated over the launches recorded since pf_profile_kernels_enable; the caller must have
+// synchronised the stream.  Returns the number of bytes written (excluding the terminating NUL) or a negative status.
+int pf_profile_kernels_read(pf_handle h, char* buf, int cap) {
+  if (!h || !buf || cap < 1) return fail(PF_ERR_ARG, "pf_profile_kernels_read: bad argument");
+  std::map<std::string, std::pair<int, double>> agg;
+  std::vector<std::string> order;
+  for (const auto& r : g_kp.recs) {
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, r.a, r.b));
+    const char* c = r.expr;
+    while (*c == '(' || *c == ' ') ++c;
+    const char* e = c;
+    while (*e && (isalnum((unsigned char)*e) || *e == '_')) ++e;
+    std::string name(c, e);
+    // template arguments of direct kernel launches distinguish the variants (e.g. stem_conv_launch<7, 7, 2, 3, 64>)
+    if (*e == '<' && e[1] != '<') { const char* t = strchr(e, '>'); if (t) name.append(e, t + 1); }
+    auto it = agg.find(name);
+    if (it == agg.end()) { order.push_back(name); it = agg.emplace(name, std::make_pair(0, 0.0)).first; }
+    it->second.first += 1;
+    it->second.second += ms;
+  }
+  std::string out = "kernel,launches,ms\n";
+  for (const auto& n : order) {
+    char line[256];
+    snprintf(line, sizeof line, "%s,%d,%.4f\n", n.c_str(), agg[n].first, agg[n].second);
+    out += line;
+  }
+  if ((int)out.size() + 1 > cap) return fail(PF_ERR_ARG, "pf_profile_kernels_read: buffer too small (%d needed)", (int)out.size() + 1);
+  memcpy(buf, out.c_str(), out.size() + 1);
+  g_kp.used = 0;
+  g_kp.recs.clear();
+  return (int)out.size();
 }
 int pf_set_option(pf_handle h, const char* name, int value) {
   if (!h || !name) return fail(PF_ERR_ARG, "pf_set_option: null argument");
@@ -1276,7 +1354,7 @@ int pf_op_dwconv3x3_gelu(const float* x, float* y, int B, int H, int W, int C, c
 }
 int pf_op_dwconv7x7(const float* x, float* y, int B, int H, int W, int C, const float* w, const float* bias, void* stream) {
   if (C % 4) return fail(PF_ERR_ARG, "C %% 4");
-  LAUNCHED((dwconv7x7_kernel<<<ew_grid((long long)B * H * ((W + 3) / 4) * (C / 4)), 256, 0, (cudaStream_t)stream>>>(x, y, B, H, W, C, w, bias), cudaGetLastError()));
+  LAUNCHED((dwconv7x7_kernel<<<ew_grid((long long)B * ((H + 1) / 2) * ((W + 7) / 8) * (C / 4)), 256, 0, (cudaStream_t)stream>>>(x, y, B, H, W, C, w, bias), cudaGetLastError()));
   return PF_OK;
 }
 int pf_op_upsample2x(const float* x, float* y, int B, int H, int W, int C, void* stream) {
