@@ -97,3 +97,49 @@ def test_compat_alias():
     assert PerspectiveFields is pkg.PerspectiveFields and "PersNet-360Cities" in model_zoo
     sys.modules.pop("perspective2d", None)
     sys.modules.pop("perspective2d.perspectivefields", None)
+
+
+def test_gelu_polynomial_in_the_kernels_matches_erf():
+    """csrc/common.cuh:gelu_erf evaluates erf through a degree-8 polynomial for log2 erfc and one ex2.  The coefficients are
+    read from the source and the same fp32 arithmetic is replayed here against scipy's erf in float64: the error must stay at
+    the level of fp32 rounding (the libm erff route measures 4.5e-7 on the same grid)."""
+    import math
+    import os
+    import re
+    import numpy as np
+    from scipy.special import erf
+    src = open(os.path.join(os.path.dirname(__file__), "..", "perspectivefields_b200", "csrc", "common.cuh")).read()
+    body = src[src.index("float gelu_erf(float x)"):]
+    body = body[body.index("#else"):body.index("#endif")]
+    zmax = float(re.search(r"fminf\(fabsf\(x\) \* [0-9.]+f, ([0-9.]+)f\)", body).group(1))
+    lead = float(re.search(r"float q = (-?[0-9.e+-]+)f;", body).group(1))
+    rest = [float(m) for m in re.findall(r"q = fmaf\(q, z, (-?[0-9.e+-]+)f\);", body)]
+    assert len(rest) == 8
+    f32 = np.float32
+    x = np.linspace(-12, 12, 2_000_001).astype(f32)
+    z = np.minimum(np.abs(x) * f32(0.70710678118654752440), f32(zmax))
+    q = np.full_like(z, f32(lead))
+    for c in rest:
+        q = q * z + f32(c)
+    ec = np.exp2(q).astype(f32)
+    g = (f32(0.5) * x * (f32(1) + np.copysign(f32(1) - ec, x))).astype(np.float64)
+    xd = x.astype(np.float64)
+    exact = 0.5 * xd * (1 + erf(xd / math.sqrt(2)))
+    err = np.abs(g - exact)
+    assert err.max() < 6e-7
+    assert (err / np.maximum(np.abs(xd), 1)).max() < 2e-7
+
+
+def test_up2_conv3_composition():
+    """weights.py:_compose_up2_conv3: conv3x3(pad 1) o bilinear x2 equals four 3x3 phase convolutions on the low-res grid
+    everywhere except the two outermost output rows / columns (those are recomputed by conv1_ring_kernel)."""
+    import torch.nn.functional as F
+    from perspectivefields_b200.weights import _compose_up2_conv3
+    torch.manual_seed(0)
+    x = torch.randn(2, 6, 9, 11, dtype=torch.float64)
+    w = torch.randn(5, 6, 3, 3, dtype=torch.float64)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False), w, padding=1)
+    y = F.conv2d(x, _compose_up2_conv3(w), padding=1)              # [2, 4*5, 9, 11], row = (py*2+px)*5 + o
+    y = y.view(2, 2, 2, 5, 9, 11).permute(0, 3, 4, 1, 5, 2).reshape(2, 5, 18, 22)
+    assert (y - ref)[:, :, 2:-2, 2:-2].abs().max() < 1e-12
+    assert (y - ref).abs().max() > 1e-3                            # the ring really differs: it needs the exact kernel
