@@ -399,6 +399,20 @@ def main():
                                                      "launches_per_step": prof[3 * c + 2] / args.steps} for c in range(NC) if prof[3 * c + 2] > 0},
     }
 
+    # HBM-bound tail of the path (the "decode-head" HBM roofline applies to the write-out stage): resample of the
+    # three 320x320 fields to the original sizes + normalise / asin.  Algorithmic bytes = 4*(3*320*320 read + 3*H*W written) per image.
+    roofline_post = None
+    pk_post = per_kernel.get("postprocess_kernel")
+    if pk_post and pk_post["ms_per_step"] > 0:
+        post_bytes = sum(4 * (3 * 320 * 320 + 3 * int(h_) * int(w_)) for h_, w_ in zip(heights, widths))
+        hbm_peak = peaks.get("hbm_gbs") or 6500.0
+        gbps = post_bytes / (pk_post["ms_per_step"] / 1000.0) / 1e9
+        roofline_post = {"bound": "hbm", "kernel": "postprocess_kernel (bilinear resample to (H,W) + F.normalize / asin, all images in one launch)",
+                         "achieved": gbps, "peak": hbm_peak, "unit": "GB/s", "frac": gbps / hbm_peak, "bytes_per_step": post_bytes,
+                         "ms_per_step": pk_post["ms_per_step"],
+                         "note": "in-pipeline CUDA-event time of the per-kernel pass (includes ~4 us of event overhead); a 150 MB launch is "
+                                 "too short to reach the streaming peak, and the kernel is instruction-bound by asin / normalise (profiles/)"}
+
     # ---------------- CPU baseline: oracle port of the reference on the host cores (rank 0, N = 1 only) ---------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -419,6 +433,7 @@ def main():
             "gpu_launches": int(launches),
             "host_enqueue_ms_per_step": host_enqueue_ms, "host_pf_forward_ms_per_step": host_fwd * 1000 / args.steps,
             "roofline": roofline,
+            "roofline_post": roofline_post,
             "per_kernel": per_kernel,
             "cpu_baseline": cpu,
         }), flush=True)
