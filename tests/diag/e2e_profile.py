@@ -1,7 +1,7 @@
 """Host-side time breakdown of one end-to-end step (bench.py's e2e leg): where does the Python thread spend its time?
-usage: python tools/e2e_profile.py [batch]"""
+usage: python tests/diag/e2e_profile.py [batch]"""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
 import pf_test_util as U

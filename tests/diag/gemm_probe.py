@@ -1,6 +1,6 @@
 """GPU: time (and let ncu capture) single GEMM-engine launches of chosen shapes through pf_op_conv_gemm engine 3."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 import pf_test_util as U

@@ -1,6 +1,6 @@
 """GPU: first contact with the tcgen05 kernel -- prints relative errors, never asserts."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch, torch.nn.functional as F
 import pf_test_util as U
