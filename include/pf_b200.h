@@ -121,6 +121,21 @@ const char* pf_debug_name(pf_handle h, int i);
 int64_t pf_debug_numel(pf_handle h, const char* name);
 int pf_debug_copy(pf_handle h, const char* name, float* dst_dev, int64_t numel, void* stream);
 
+/* ---- camera parameters -> dense perspective fields -------------------------------------
+ * Replaces PanoCam.get_up_general / PanoCam.get_lat_general (perspective2d/utils/panocam.py:451-513, :515-556), which callers
+ * evaluate right after the inference path on ParamNet's output (utils/utils.py:367-385, demo/demo.py:69-78).  One launch per
+ * 24 images; float64 arithmetic, float32 results.  No engine handle: the function has no weights. */
+typedef struct pf_camera {
+  int32_t height, width;        /* im_h, im_w */
+  double focal_rel;             /* focal length / image height */
+  double elevation, roll;       /* radians */
+  double cx_rel, cy_rel;        /* principal point: pixel / size - 0.5 */
+  int64_t up_offset;            /* float offset of this image's [H,W,2] (x,y) block in `up` */
+  int64_t lat_offset;           /* float offset of this image's [H,W] block (degrees) in `lat` */
+} pf_camera;
+/* cams: HOST array of n descriptors; up / lat: DEVICE blobs (either may be NULL to skip that field). */
+int pf_camera_fields(int device, const pf_camera* cams, int n, float* up, float* lat, void* stream);
+
 /* ---- single-operator entry points (unit tests; the same kernels pf_forward launches) -------------------- */
 
 /* Implicit-GEMM conv / linear on NHWC fp32, bf16x3 split precision.  x: [B,H,W,Cin]; whi/wlo: bf16 [N][KH*KW*Cin]

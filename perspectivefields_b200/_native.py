@@ -25,6 +25,13 @@ class pf_model_desc(ctypes.Structure):
                 ("param_input_size", ctypes.c_int), ("pixel_mean", ctypes.c_float * 3), ("pixel_std", ctypes.c_float * 3)]
 
 
+class pf_camera(ctypes.Structure):
+    """include/pf_b200.h: struct pf_camera."""
+    _fields_ = [("height", ctypes.c_int32), ("width", ctypes.c_int32), ("focal_rel", ctypes.c_double), ("elevation", ctypes.c_double),
+                ("roll", ctypes.c_double), ("cx_rel", ctypes.c_double), ("cy_rel", ctypes.c_double),
+                ("up_offset", ctypes.c_int64), ("lat_offset", ctypes.c_int64)]
+
+
 class pf_batch(ctypes.Structure):
     _fields_ = [("n", ctypes.c_int),
                 ("images_u8", ctypes.c_void_p), ("image_offset", ctypes.POINTER(ctypes.c_int64)),
@@ -99,6 +106,7 @@ def lib():
         "pf_debug_copy": (i32, [vp, ctypes.c_char_p, vp, i64, vp]),
         "pf_op_conv_gemm": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp, i32, vp]),
         "pf_set_option": (i32, [vp, ctypes.c_char_p, i32]),
+        "pf_camera_fields": (i32, [i32, ctypes.POINTER(pf_camera), i32, vp, vp, vp]),
         "pf_op_layernorm": (i32, [vp, vp, i64, i32, vp, vp, f32, vp]),
         "pf_op_attention": (i32, [vp, vp, vp, i32, i32, i32, i32, vp]),
         "pf_op_attention_mma": (i32, [vp, vp, vp, i32, i32, i32, i32, vp]),
@@ -123,7 +131,7 @@ def lib():
 
 EXPORTS = ["pf_abi_version", "pf_last_error", "pf_kernel_launch_count", "pf_create", "pf_destroy", "pf_set_weight",
            "pf_finalize", "pf_workspace_bytes", "pf_forward", "pf_profile_enable", "pf_profile_read", "pf_profile_kernels_enable", "pf_profile_kernels_read", "pf_set_option", "pf_debug_enable", "pf_debug_count", "pf_debug_name",
-           "pf_debug_numel", "pf_debug_copy", "pf_op_conv_gemm", "pf_op_layernorm", "pf_op_attention", "pf_op_attention_mma",
+           "pf_debug_numel", "pf_debug_copy", "pf_camera_fields", "pf_op_conv_gemm", "pf_op_layernorm", "pf_op_attention", "pf_op_attention_mma",
            "pf_op_dwconv3x3_gelu", "pf_op_dwconv7x7", "pf_op_upsample2x", "pf_op_preprocess"]
 
 

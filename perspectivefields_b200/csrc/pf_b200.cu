@@ -7,6 +7,7 @@
 
 #include <atomic>
 #include <cctype>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -1333,6 +1334,33 @@ int pf_op_conv_gemm(const float* x, int B, int H, int W, int Cin, const void* wh
   LAUNCHED(conv_gemm_launch(p, (cudaStream_t)stream));
   return PF_OK;
 }
+int pf_camera_fields(int device, const pf_camera* cams, int n, float* up, float* lat, void* stream) {
+  if (!cams || n < 1 || (!up && !lat)) return fail(PF_ERR_ARG, "pf_camera_fields: bad argument");
+  CU(cudaSetDevice(device));
+  for (int i0 = 0; i0 < n; i0 += kCamChunk) {
+    const int m = n - i0 < kCamChunk ? n - i0 : kCamChunk;
+    CamBatch b{};
+    long long max_px = 1;
+    for (int i = 0; i < m; ++i) {
+      const pf_camera& c = cams[i0 + i];
+      if (c.height < 1 || c.width < 1 || !(c.focal_rel != 0.0)) return fail(PF_ERR_ARG, "pf_camera_fields: image %d: size %dx%d, focal %g", i0 + i, c.height, c.width, c.focal_rel);
+      if ((c.up_offset & 1) != 0) return fail(PF_ERR_ARG, "pf_camera_fields: up_offset must be even (8-byte stores)");
+      CamImage& o = b.im[i];
+      o.H = c.height; o.W = c.width;
+      o.f = c.focal_rel * c.height;
+      o.cx = (c.cx_rel + 0.5) * c.width; o.cy = (c.cy_rel + 0.5) * c.height;
+      o.sr = sin(c.roll); o.cr = cos(c.roll); o.se = sin(c.elevation); o.ce = cos(c.elevation);
+      o.sgn = c.elevation > 0 ? 1.0 : (c.elevation < 0 ? -1.0 : 0.0);
+      o.up_off = c.up_offset; o.lat_off = c.lat_offset;
+      const long long px = (long long)c.height * c.width;
+      if (px > max_px) max_px = px;
+    }
+    const dim3 grid((unsigned)cdivl(max_px, 256), (unsigned)m);
+    LAUNCHED((camera_fields_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(b, up, lat), cudaGetLastError()));
+  }
+  return PF_OK;
+}
+
 int pf_op_layernorm(const float* x, float* y, int64_t rows, int C, const float* w, const float* b, float eps, void* stream) {
   LAUNCHED(layernorm_launch(x, y, rows, C, w, b, eps, (cudaStream_t)stream));
   return PF_OK;

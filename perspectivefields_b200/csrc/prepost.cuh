@@ -204,4 +204,52 @@ __global__ void __launch_bounds__(256) postprocess_kernel(const float* __restric
   (void)n; (void)total;
 }
 
+// =====================================================================================================
+// Camera parameters -> dense perspective fields: PanoCam.get_up_general / get_lat_general
+// (utils/panocam.py:451-556), what callers evaluate right after the inference path (utils/utils.py:367-385).
+// One thread per pixel, float64 arithmetic like the numpy reference, float32 results; the kernel is bound by its stores.
+//   up  [H, W, 2] (x, y): unit vector from the pixel centre (j + .5, i + .5) to the vertical vanishing point, flipped by
+//                sign(elevation); the constant (-sin roll, -cos roll) when elevation == 0 exactly (:488)
+//   lat [H, W] degrees: ray ((dx, dy, f) / f) rotated by roll, then elevation; -atan2(y_w, hypot(x_w, z_w)); dx / dy sample
+//                linspace(-cx, W - cx, W) INCLUDING both end points (:534-539: spacing W / (W - 1), not pixel centres)
+struct CamImage {
+  int H, W;
+  double f, cx, cy;           // focal length in pixels, principal point in pixels
+  double sr, cr, se, ce;      // sin / cos of roll and elevation (computed on the host in float64)
+  double sgn;                 // sign(elevation): +1, -1 or 0 (0 selects the constant field)
+  long long up_off, lat_off;  // float offsets of this image's blocks in the output blobs
+};
+constexpr int kCamChunk = 24;   // images per launch (the descriptors travel as a kernel parameter)
+struct CamBatch { CamImage im[kCamChunk]; };
+
+__global__ void __launch_bounds__(256) camera_fields_kernel(const __grid_constant__ CamBatch batch, float* __restrict__ up, float* __restrict__ lat) {
+  const CamImage& c = batch.im[blockIdx.y];
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= (long long)c.H * c.W) return;
+  const int i = (int)(p / c.W), j = (int)(p - (long long)i * c.W);
+  if (up) {
+    double vx, vy;
+    if (c.sgn == 0.0) { vx = -c.sr; vy = -c.cr; }
+    else {
+      const double vvp_x = (c.sr * c.ce * c.f) / -c.se + c.cx, vvp_y = (c.cr * c.ce * c.f) / -c.se + c.cy;
+      vx = (vvp_x - ((double)j + 0.5)) * c.sgn;
+      vy = (vvp_y - ((double)i + 0.5)) * c.sgn;
+    }
+    const double n = sqrt(vx * vx + vy * vy);
+    *reinterpret_cast<float2*>(up + c.up_off + 2 * p) = make_float2((float)(vx / n), (float)(vy / n));
+  }
+  if (lat) {
+    // numpy.linspace(start, stop, num): start + k * ((stop - start) / (num - 1)), last sample = stop exactly
+    const double x0 = (-c.W / 2.0) - (c.cx - (c.W / 2.0)), x1 = (c.W / 2.0) - (c.cx - (c.W / 2.0));
+    const double y0 = (-c.H / 2.0) - (c.cy - (c.H / 2.0)), y1 = (c.H / 2.0) - (c.cy - (c.H / 2.0));
+    const double dx = c.W == 1 ? x0 : (j == c.W - 1 ? x1 : (double)j * ((x1 - x0) / (double)(c.W - 1)) + x0);
+    const double dy = c.H == 1 ? y0 : (i == c.H - 1 ? y1 : (double)i * ((y1 - y0) / (double)(c.H - 1)) + y0);
+    const double x = dx / c.f, y = dy / c.f;
+    const double xw = x * c.cr - y * c.sr;
+    const double yw = x * c.ce * c.sr + y * c.ce * c.cr - c.se;
+    const double zw = x * c.se * c.sr + y * c.se * c.cr + c.ce;
+    lat[c.lat_off + p] = (float)(-atan2(yw, sqrt(xw * xw + zw * zw)) / 3.14159265358979323846 * 180.0);
+  }
+}
+
 }  // namespace pf
