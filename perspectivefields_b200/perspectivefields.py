@@ -145,6 +145,20 @@ class _Engine:
         return out
 
 
+class ResizeTransform:
+    """The ``aug`` attribute of the reference class (perspectivefields.py:16-67, built at :155): target size and PIL filter of
+    the input resize.  Here the resize itself runs inside the CUDA pre-process (Pillow-exact integer arithmetic,
+    csrc/prepost.cuh:preprocess_kernel), so the object only carries the parameters; ``apply_image`` points there."""
+
+    def __init__(self, new_h, new_w, interp=None):
+        self.new_h, self.new_w = new_h, new_w
+        self.interp = 2 if interp is None else interp          # PIL.Image.BILINEAR == 2
+
+    def apply_image(self, img, interp=None):
+        raise NotImplementedError("the 320x320 resize is part of the CUDA pre-process of PerspectiveFields.inference / "
+                                  "inference_batch; it is not available as a separate host-side transform")
+
+
 class PerspectiveFields(nn.Module):
     def __init__(self, version="Paramnet-360Cities-edina-centered"):
         super().__init__()
@@ -159,6 +173,7 @@ class PerspectiveFields(nn.Module):
         self.freeze = self.cfg.MODEL.FREEZE
         self.debug_on = self.cfg.DEBUG_ON
         self.input_format = self.cfg.INPUT.FORMAT
+        self.aug = ResizeTransform(RESIZE[0], RESIZE[1])
         self._schema = dict(checkpoint_schema(version))
         self._ref_state = default_state(version)   # reference-layout weights, host side
         self._engine = None

@@ -66,6 +66,7 @@ def test_model_surface_without_gpu():
     m, sd = U.make_model("PersNet_Paramnet-GSV-centered", seed=2, device=None)
     assert m.version == "PersNet_Paramnet-GSV-centered" and m.param_on is True and m.input_format == "BGR"
     assert m.cfg.MODEL.RECOVER_RPF is True and m.cfg.MODEL.RECOVER_PP is False and m.cfg.DATALOADER.RESIZE == [320, 320]
+    assert (m.aug.new_h, m.aug.new_w, m.aug.interp) == (320, 320, 2)     # perspectivefields.py:155; PIL.Image.BILINEAR == 2
     got = m.state_dict()
     assert list(got) == [k for k, _ in oschema.state_dict_schema(m.version)]
     assert all(torch.equal(got[k], sd[k]) for k in sd)
