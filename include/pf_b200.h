@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PF_ABI_VERSION 1
+#define PF_ABI_VERSION 2
 
 typedef struct pf_engine* pf_handle;
 
@@ -92,9 +92,9 @@ int64_t pf_workspace_bytes(pf_handle h, int n, int max_h);
 int pf_forward(pf_handle h, const pf_batch* batch, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Per-launch timing of the GEMM engine with CUDA events on the launch stream (bench.py roofline leg).  pf_profile_read
- * fills out21[cfg*3 + {0,1,2}] = {milliseconds, algorithmic FLOPs (2*M*N*K), launches} for the seven engine configurations
- * (0-2: HMMA 128x{128,64,32}, 3: tcgen05 generic (register-staged A), 4: tcgen05 halo 3x3 (register-staged A),
- *  5: TMA+tcgen05 GEMM, 6: TMA+tcgen05 halo 3x3) accumulated since the previous read; synchronise the stream first. */
+ * fills out21[cfg*3 + {0,1,2}] = {milliseconds, algorithmic FLOPs (2*M*N*K), launches} per engine configuration (slots 0-4 are
+ * unused since ABI 2 -- the earlier HMMA / register-staged engines were removed; 5: TMA+tcgen05 GEMM mode, 6: TMA+tcgen05 halo
+ * 3x3 mode) accumulated since the previous read; synchronise the stream first. */
 int pf_profile_enable(pf_handle h, int on /* 0 off, 1 on, n > 1: on + pre-create events for n GEMM launches */);
 int pf_profile_read(pf_handle h, double* out21);
 /* A CUDA-event pair around EVERY kernel launch of the forward graph: in-pipeline time per kernel (bench.py "per_kernel").
@@ -103,14 +103,16 @@ int pf_profile_read(pf_handle h, double* out21);
 int pf_profile_kernels_enable(pf_handle h, int max_launches);
 int pf_profile_kernels_read(pf_handle h, char* buf, int cap);
 
-/* Engine options.  "tma" (default 1): the forward graph runs on the persistent TMA -> tcgen05 -> TMEM engine with pre-split
- * bf16 hi/lo activations (gemm_tma.cuh).  With "tma" = 0 the earlier engines are used (fp32 activations split on the fly):
- * "tcgen05" (default 1) selects the register-staged tcgen05 kernels over the warp-level HMMA kernel, "halo3x3" (default 1)
- * the halo-tile variant for 3x3/stride-1 convolutions.  All engines evaluate the same bf16x3 products.
- * "attn_mma" (default 1, TMA graph only): attention core on the tensor cores (attention_mma.cuh) instead of CUDA cores.
- * "stem_tc" (default 1, TMA graph only): the two 7x7 stems as patch gather + TMA GEMM instead of fp32 direct convolution.
- * "phase_conv1" (default 1, TMA graph only): conv_fuse_conv1 composed with the x2 bilinear upsample in front of it (four output
- *   phases on the 160x160 grid + an exact fp32 border-ring kernel); 0 = materialise the upsampled tensor, conv at 320x320. */
+/* Engine options (all default 1 unless noted; the whole graph runs on the persistent TMA -> tcgen05 -> TMEM engine with pre-split
+ * bf16 hi/lo activations, gemm_tma.cuh):
+ * "attn_mma": attention core on the tensor cores (attention_mma.cuh) instead of the exact-softmax CUDA-core kernel.
+ * "attn_split": q / kv leave their GEMMs as split planes (0 = fp32, split inside the attention kernel).
+ * "stem_tc": the two 7x7 stems as patch gather + TMA GEMM instead of fp32 direct convolution.
+ * "phase_conv1": conv_fuse_conv1 composed with the x2 bilinear upsample in front of it (four output phases on the 160x160 grid
+ *   + an exact fp32 border-ring kernel); 0 = materialise the upsampled tensor, conv at 320x320.
+ * "decode_only" (default 0; classification heads): the 73 / 180 logits are never written -- the 1x1 prediction
+ *   conv, argmax and bin decode (gravity_head.py:243-244 + utils/utils.py:114-130, latitude_head.py:205-208 + utils.py:148-162)
+ *   run in one kernel and pred_gravity / pred_latitude receive the decoded fields [n,2,320,320] / [n,1,320,320] (degrees). */
 int pf_set_option(pf_handle h, const char* name, int value);
 
 /* Debug taps (tests only): when enabled, intermediates of the next pf_forward are kept (never recycled) and can be
@@ -136,14 +138,40 @@ typedef struct pf_camera {
 /* cams: HOST array of n descriptors; up / lat: DEVICE blobs (either may be NULL to skip that field). */
 int pf_camera_fields(int device, const pf_camera* cams, int n, float* up, float* lat, void* stream);
 
+/* ---- multi-GPU gather of results (one process per GPU; NCCL point-to-point over NVLink) ---------------------
+ * inference_batch shards its list over the ranks; the per-image results live on each rank's device and are gathered to ONE
+ * rank with grouped ncclSend / ncclRecv enqueued on the caller's stream (so that the gather of micro-batch k overlaps the
+ * forward of micro-batch k+1 when issued on a side stream).  NCCL is resolved at run time from the process
+ * (libnccl.so.2 -- the one PyTorch ships); the 128-byte unique id is created on rank 0 and distributed by the caller
+ * (torch.distributed / MPI / a file: plumbing). */
+typedef struct pf_comm* pf_comm_handle;
+int pf_comm_unique_id(void* id128);                                              /* rank 0: ncclGetUniqueId -> 128 bytes */
+int pf_comm_create(int device, int rank, int nranks, const void* id128, pf_comm_handle* out);
+int pf_comm_destroy(pf_comm_handle c);
+/* One grouped exchange.  On every rank != root: send `count` segments (DEVICE pointer, bytes) to root.  On root: receive
+ * `count` segments, segment i from rank peer[i].  All segments of one call travel in one ncclGroup on `stream`. */
+int pf_gather(pf_comm_handle c, int root, int count, void* const* dev_ptrs, const int64_t* bytes, const int32_t* peer, void* stream);
+
+/* ---- decode front-end: JPEG bytes -> the device blob of BGR uint8 HWC images pf_forward reads ---------
+ * Replaces `cv2.imread` in front of the path (demo/demo.py:151) with nvJPEG (bound at run time), the images of a batch fanned out
+ * over worker threads / streams and joined into `stream`.  pf_jpeg_info parses the header only (sizes for the blob layout). */
+typedef struct pf_jpeg* pf_jpeg_handle;
+int pf_jpeg_create(int device, int max_threads /* 0 = half the host's hardware threads, at most 32 */, pf_jpeg_handle* out);
+int pf_jpeg_destroy(pf_jpeg_handle j);
+int pf_jpeg_info(pf_jpeg_handle j, const uint8_t* data, int64_t length, int32_t* height, int32_t* width);
+/* data[i] / length[i]: HOST JPEG streams; blob: DEVICE; image i is written as [height[i], width[i], 3] BGR at byte offset[i]. */
+int pf_jpeg_decode_batch(pf_jpeg_handle j, int n, const uint8_t* const* data, const int64_t* length, const int32_t* height,
+                         const int32_t* width, uint8_t* blob, const int64_t* offset, void* stream);
+
 /* ---- single-operator entry points (unit tests; the same kernels pf_forward launches) -------------------- */
 
-/* Implicit-GEMM conv / linear on NHWC fp32, bf16x3 split precision.  x: [B,H,W,Cin]; whi/wlo: bf16 [N][KH*KW*Cin]
+/* Conv / linear on NHWC fp32 on the TMA -> tcgen05 engine, bf16x3 split precision (the input is split into hi/lo planes first,
+ * as a producer kernel of the forward graph would; 3x3/s1/p1 with Cin % 64 == 0 -> halo mode, 1x1 -> GEMM mode, else patch gather).  x: [B,H,W,Cin]; whi/wlo: bf16 [N][KH*KW*Cin]
  * ordered (ky,kx,ci); bias: [N] or NULL; res: [B,OH,OW,N] or NULL; y: [B,OH,OW,N].
  * y = act(conv(relu_in?(x)) + bias) (+ relu_res?(res));  act: 0 none, 1 ReLU, 2 GELU. */
 int pf_op_conv_gemm(const float* x, int B, int H, int W, int Cin, const void* whi, const void* wlo, const float* bias,
                     int N, int KH, int KW, int stride, int pad, int in_relu, int act, const float* res, int res_relu,
-                    float* y, int engine /* 0 = HMMA, 1 = tcgen05 generic, 2 = tcgen05 halo-tile 3x3, 3 = TMA engine */, void* stream);
+                    float* y, void* stream);
 int pf_op_layernorm(const float* x, float* y, int64_t rows, int C, const float* w, const float* b, float eps, void* stream);
 int pf_op_attention(const float* q, const float* kv, float* out, int B, int N, int C, int heads, void* stream);      /* CUDA-core fp32 */
 int pf_op_attention_mma(const float* q, const float* kv, float* out, int B, int N, int C, int heads, void* stream);  /* tensor cores, bf16x3 */
@@ -152,6 +180,23 @@ int pf_op_dwconv7x7(const float* x, float* y, int B, int H, int W, int C, const 
 int pf_op_upsample2x(const float* x, float* y, int B, int H, int W, int C, void* stream);
 /* Pillow-exact resize + normalise of ONE uint8 HWC image -> [320,320,4] fp32 (b,g,r,0). */
 int pf_op_preprocess(const uint8_t* img_dev, int H, int W, const float* mean3, const float* std3, float* y, void* stream);
+/* ResizeTransform.apply_image (perspectivefields.py:34-67) on the device, HWC in -> HWC out, C channels:
+ *   uint8 (PIL branch, :38-46): Pillow-exact antialiased bilinear (the same integer kernel as pf_forward's pre-process);
+ *   float32 (:47-66): F.interpolate(mode="bilinear", align_corners=False), no antialias. */
+int pf_op_resize_u8(const uint8_t* img_dev, int H, int W, int new_h, int new_w, uint8_t* out_dev, void* stream);   /* C = 3 */
+int pf_op_resize_f32(const float* img_dev, int H, int W, int C, int new_h, int new_w, float* out_dev, void* stream);
+/* argmax over channels + bin decode of NCHW logits [B,NC,HW] (gravity_head.py:243-244 + utils/utils.py:114-130 when
+ * is_gravity, field [B,2,HW]; latitude_head.py:205-208 + utils/utils.py:148-162 otherwise, field [B,1,HW] in degrees). */
+int pf_op_argmax_decode(const float* logits, float* field, int B, int HW, int NC, int is_gravity, void* stream);
+/* the same decode WITHOUT materialised logits (option "decode_only"): 1x1 conv 32 -> NC on feat [B*HW, ld] (channels coff..coff+31,
+ * weights [NC][32], bias [NC]) + argmax + bin decode in one kernel; logits bit-identical to the separate 1x1 conv kernel. */
+int pf_op_pred_argmax_decode(const float* feat, int ld, int coff, const float* w, const float* bias, float* field, int B, int HW, int NC,
+                             int is_gravity, void* stream);
+/* resample of decoded fields to the original sizes (gravity_head.py:246-256, latitude_head.py:209-219, utils/utils.py:483-507):
+ * vec [n,2,320,320], lat [n,1,320,320] -> blobs as in pf_batch; lat_is_sin: lat holds sin(latitude) (regression head). */
+int pf_op_postprocess(const float* vec, const float* lat, int n, const int32_t* height, const int32_t* width,
+                      float* gravity_original, const int64_t* gravity_original_offset, float* latitude_original,
+                      const int64_t* latitude_original_offset, int lat_is_sin, void* stream);
 
 #ifdef __cplusplus
 }

@@ -283,6 +283,27 @@ def preprocess(img_bgr):
     return torch.as_tensor(image.astype("float32").transpose(2, 0, 1))
 
 
+def resize_float(img, new_h, new_w):
+    """perspectivefields.py:47-66, the non-uint8 branch of ResizeTransform.apply_image: HW(C) numpy -> NCHW torch ->
+    ``F.interpolate(mode="bilinear", align_corners=False)`` (no antialias) -> HW(C) numpy of the input dtype."""
+    if any(x < 0 for x in img.strides):
+        img = np.ascontiguousarray(img)
+    t = torch.from_numpy(img)
+    shape = list(t.shape)
+    shape_4d = shape[:2] + [1] * (4 - len(shape)) + shape[2:]
+    t = t.view(shape_4d).permute(2, 3, 0, 1)
+    t = F.interpolate(t, (new_h, new_w), mode="bilinear", align_corners=False)
+    shape[:2] = (new_h, new_w)
+    return t.permute(2, 3, 0, 1).view(shape).numpy()
+
+
+def inference_float(sd, version, img_bgr):
+    """perspectivefields.py:194-205 for a non-uint8 image: float resize branch, then ``astype("float32")`` and forward."""
+    image = resize_float(img_bgr.copy(), NET_H, NET_W)
+    image = torch.as_tensor(image.astype("float32").transpose(2, 0, 1))
+    return forward(sd, version, [{"image": image, "height": img_bgr.shape[0], "width": img_bgr.shape[1]}])[0]
+
+
 @torch.no_grad()
 def forward(sd, version, batched_inputs, taps=None):
     """perspectivefields.py:223-272 on CPU fp32.  ``batched_inputs``: list of {"image","height","width"}."""

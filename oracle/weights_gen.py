@@ -23,7 +23,7 @@ def _rs(key, seed):
     return np.random.RandomState((zlib.crc32(key.encode()) ^ (seed * 2654435761)) & 0x7FFFFFFF)
 
 
-def synth_tensor(key, shape, seed=0):
+def synth_tensor(key, shape, seed=0, gravity_bias=(0.30, -0.80), gravity_gain=0.08):
     rs = _rs(key, seed)
     if key.endswith("num_batches_tracked"):
         return torch.tensor(1000, dtype=torch.int64)
@@ -46,7 +46,7 @@ def synth_tensor(key, shape, seed=0):
         elif modleaf == "linear_pred_gravity" and shape[0] == 2:
             # a trained regression head emits near-unit up-vectors; keep |v| away from 0 so that the
             # F.normalize that follows is as well conditioned as it is in deployment
-            t = np.array([0.30, -0.80], dtype=np.float32)
+            t = np.array(gravity_bias, dtype=np.float32)
         else:
             t = 0.1 * n
     else:
@@ -59,16 +59,20 @@ def synth_tensor(key, shape, seed=0):
         elif modleaf == "linear_pred_latitude" and shape[0] == 1:
             gain = 0.04  # keep sin(latitude) mostly inside (-1, 1); calibrated in tests/golden/make_golden.py
         elif modleaf == "linear_pred_gravity" and shape[0] == 2:
-            gain = 0.08
+            gain = gravity_gain
         elif mod == "param_net.backbone.head":
             gain = 0.3
         t = n * (gain / math.sqrt(fan_in))
     return torch.from_numpy(np.ascontiguousarray(t, dtype=np.float32))
 
 
-def synth_state_dict(version, seed=0):
-    """``OrderedDict``-like dict with the reference's key names and shapes."""
-    return {k: synth_tensor(k, s, seed) for k, s in state_dict_schema(version)}
+def synth_state_dict(version, seed=0, gravity_bias=(0.30, -0.80), gravity_gain=0.08):
+    """``OrderedDict``-like dict with the reference's key names and shapes.
+
+    ``gravity_bias=(0, 0)`` with a larger ``gravity_gain`` gives a regression gravity head whose output is driven by the weights
+    alone: the normalised field then turns through all directions and |v_raw| comes close to 0 at some pixels (the parity tests
+    mask those), instead of the near-constant field of the default checkpoint."""
+    return {k: synth_tensor(k, s, seed, gravity_bias, gravity_gain) for k, s in state_dict_schema(version)}
 
 
 def synth_images(n, h, w, seed=0):

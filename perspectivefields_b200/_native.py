@@ -17,7 +17,7 @@ PF_F32, PF_BF16 = 0, 1
 PF_PARAM_NONE, PF_PARAM_CENTERED, PF_PARAM_UNCENTERED = 0, 1, 2
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-shared", "-ldl"]
 
 
 class pf_model_desc(ctypes.Structure):
@@ -104,7 +104,7 @@ def lib():
         "pf_debug_name": (ctypes.c_char_p, [vp, i32]),
         "pf_debug_numel": (i64, [vp, ctypes.c_char_p]),
         "pf_debug_copy": (i32, [vp, ctypes.c_char_p, vp, i64, vp]),
-        "pf_op_conv_gemm": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp, i32, vp]),
+        "pf_op_conv_gemm": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp, vp]),
         "pf_set_option": (i32, [vp, ctypes.c_char_p, i32]),
         "pf_camera_fields": (i32, [i32, ctypes.POINTER(pf_camera), i32, vp, vp, vp]),
         "pf_op_layernorm": (i32, [vp, vp, i64, i32, vp, vp, f32, vp]),
@@ -114,6 +114,21 @@ def lib():
         "pf_op_dwconv7x7": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp]),
         "pf_op_upsample2x": (i32, [vp, vp, i32, i32, i32, i32, vp]),
         "pf_op_preprocess": (i32, [vp, i32, i32, ctypes.POINTER(f32), ctypes.POINTER(f32), vp, vp]),
+        "pf_op_resize_u8": (i32, [vp, i32, i32, i32, i32, vp, vp]),
+        "pf_op_resize_f32": (i32, [vp, i32, i32, i32, i32, i32, vp, vp]),
+        "pf_op_argmax_decode": (i32, [vp, vp, i32, i32, i32, i32, vp]),
+        "pf_op_pred_argmax_decode": (i32, [vp, i32, i32, vp, vp, vp, i32, i32, i32, i32, vp]),
+        "pf_op_postprocess": (i32, [vp, vp, i32, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), vp, ctypes.POINTER(i64), vp,
+                                    ctypes.POINTER(i64), i32, vp]),
+        "pf_comm_unique_id": (i32, [vp]),
+        "pf_comm_create": (i32, [i32, i32, i32, vp, ctypes.POINTER(vp)]),
+        "pf_comm_destroy": (i32, [vp]),
+        "pf_gather": (i32, [vp, i32, i32, ctypes.POINTER(vp), ctypes.POINTER(i64), ctypes.POINTER(ctypes.c_int32), vp]),
+        "pf_jpeg_create": (i32, [i32, i32, ctypes.POINTER(vp)]),
+        "pf_jpeg_destroy": (i32, [vp]),
+        "pf_jpeg_info": (i32, [vp, vp, i64, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]),
+        "pf_jpeg_decode_batch": (i32, [vp, i32, ctypes.POINTER(vp), ctypes.POINTER(i64), ctypes.POINTER(ctypes.c_int32),
+                                       ctypes.POINTER(ctypes.c_int32), vp, ctypes.POINTER(i64), vp]),
     }
     for name, (res, args) in sig.items():
         try:
@@ -123,16 +138,20 @@ def lib():
                 continue
             raise
         fn.restype, fn.argtypes = res, args
-    if L.pf_abi_version() != 1:
+    if L.pf_abi_version() != 2:
         raise RuntimeError("libpf_b200.so ABI version mismatch")
     _lib = L
     return L
 
 
 EXPORTS = ["pf_abi_version", "pf_last_error", "pf_kernel_launch_count", "pf_create", "pf_destroy", "pf_set_weight",
-           "pf_finalize", "pf_workspace_bytes", "pf_forward", "pf_profile_enable", "pf_profile_read", "pf_profile_kernels_enable", "pf_profile_kernels_read", "pf_set_option", "pf_debug_enable", "pf_debug_count", "pf_debug_name",
-           "pf_debug_numel", "pf_debug_copy", "pf_camera_fields", "pf_op_conv_gemm", "pf_op_layernorm", "pf_op_attention", "pf_op_attention_mma",
-           "pf_op_dwconv3x3_gelu", "pf_op_dwconv7x7", "pf_op_upsample2x", "pf_op_preprocess"]
+           "pf_finalize", "pf_workspace_bytes", "pf_forward", "pf_profile_enable", "pf_profile_read", "pf_profile_kernels_enable",
+           "pf_profile_kernels_read", "pf_set_option", "pf_debug_enable", "pf_debug_count", "pf_debug_name", "pf_debug_numel",
+           "pf_debug_copy", "pf_camera_fields", "pf_comm_unique_id", "pf_comm_create", "pf_comm_destroy", "pf_gather",
+           "pf_jpeg_create", "pf_jpeg_destroy", "pf_jpeg_info", "pf_jpeg_decode_batch",
+           "pf_op_conv_gemm", "pf_op_layernorm", "pf_op_attention", "pf_op_attention_mma", "pf_op_dwconv3x3_gelu", "pf_op_dwconv7x7",
+           "pf_op_upsample2x", "pf_op_preprocess", "pf_op_resize_u8", "pf_op_resize_f32", "pf_op_argmax_decode",
+           "pf_op_pred_argmax_decode", "pf_op_postprocess"]
 
 
 class PfError(RuntimeError):

@@ -194,16 +194,15 @@ __global__ void __launch_bounds__(kAmThreads) attention_mma_kernel(const float* 
   }
 }
 
+inline cudaError_t attention_mma_configure_device() {   // per-device shared-memory opt-in (pf_create)
+  cudaError_t e = cudaFuncSetAttribute(attention_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAmSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAmSmem);
+  return e;
+}
+
 // q / kv: fp32 pointers, or (qs / kvs non-empty) split planes with row pitch C / 2C
 inline cudaError_t attention_mma_launch(const float* q, const float* kv, float* out, int B, int N, int C, int heads, cudaStream_t st, SplitT sp = SplitT(),
                                         SplitT qs = SplitT(), SplitT kvs = SplitT()) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAmSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAmSmem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
   if ((qs.hi != nullptr) != (kvs.hi != nullptr) || (qs.hi && (qs.ld != C || kvs.ld != 2 * C))) return cudaErrorInvalidValue;
   const int tiles = cdiv(N, kAmQTile);
   // passes per block: the grid should be about one resident wave (148 SMs x 3 blocks); the K/V staging of a block is

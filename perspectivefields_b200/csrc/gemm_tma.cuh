@@ -21,7 +21,7 @@
 #pragma once
 #include <cuda.h>
 
-#include "conv_gemm_tc.cuh"
+#include "tc_ptx.cuh"
 
 namespace pf {
 
@@ -73,7 +73,7 @@ template <int BN, int MODE, int KB> struct TmaCfg {
   static constexpr int kStages = kStagesRaw > 16 ? 16 : kStagesRaw;
   static constexpr int kSmemBytes = (MODE == MODE_HALO ? 2 * kABuf : 0) + kStages * kStage + kEpiStage + kEpiVec + 512 + 1024;
   static constexpr int kTmemCols = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
-  static constexpr uint32_t kIdesc = TcCfg<BN>::kIdesc;
+  static constexpr uint32_t kIdesc = umma_idesc_bf16(BN);
   static_assert(kStages >= 3, "ring too shallow");
   static_assert(2 * BN <= 512, "two accumulators must fit TMEM");
 };

@@ -141,6 +141,7 @@ inline cudaError_t layernorm_launch(const float* in, float* out, long long rows,
 // Block = 128 queries of one (batch, head); K and V staged in shared memory (fp32); one thread per query,
 // two passes over the keys (max, then exp/accumulate) -- fp32 CUDA-core math, exact softmax.
 constexpr int kAttnNkv = 100, kAttnD = 64, kAttnQ = 128;
+constexpr int kAttnSmem = 2 * kAttnNkv * kAttnD * 4;
 __global__ void __launch_bounds__(kAttnQ) attention_kernel(const float* __restrict__ q, const float* __restrict__ kv, float* __restrict__ out,
                                                            int N, int C, float scale, __nv_bfloat16* __restrict__ shi, __nv_bfloat16* __restrict__ slo) {
   extern __shared__ __align__(16) float s_kv[];  // K[100][64], V[100][64]
@@ -209,13 +210,7 @@ __global__ void __launch_bounds__(kAttnQ) attention_kernel(const float* __restri
 }
 
 inline cudaError_t attention_launch(const float* q, const float* kv, float* out, int B, int N, int C, int heads, cudaStream_t st, SplitT sp = SplitT()) {
-  constexpr int smem = 2 * kAttnNkv * kAttnD * 4;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  constexpr int smem = kAttnSmem;   // (> 48 KB: opted in per device by pf_create)
   dim3 grid(cdiv(N, kAttnQ), heads, B);
   attention_kernel<<<grid, kAttnQ, smem, st>>>(q, kv, out, N, C, 0.125f, sp.hi, sp.lo);
   return cudaGetLastError();
@@ -621,6 +616,23 @@ __global__ void __launch_bounds__(256) conv1_ring_kernel(const __nv_bfloat16* __
 }
 constexpr int kRingSmem = (128 * kRingPx + 2 * 64 * 32 + kRingPx * 12) * 4;
 
+// Bin decode shared by the two classification kernels (utils/utils.py:114-130 and :148-162).
+__device__ __forceinline__ void decode_bin_store(float* __restrict__ field, int b, int r, int HW, int NC, int bi, int is_gravity) {
+  if (is_gravity) {
+    // angle = (bin * (360/(NC-1)) - 180) / 180 * pi ; bin NC-1 -> (0, 0).  torch evaluates this in fp32 on an int64
+    // tensor promoted to float: bin*5.0 - 180 exact in fp32, then /180*pi.
+    float* o = field + (long long)b * 2 * HW + r;
+    if (bi == NC - 1) { o[0] = 0.f; o[HW] = 0.f; }
+    else {
+      const float ang = ((float)bi * (360.0f / (float)(NC - 1)) - 180.0f) / 180.0f * 3.14159265358979323846f;
+      o[0] = cosf(ang); o[HW] = sinf(ang);
+    }
+  } else {
+    const float bin = 180.0f / (float)NC;
+    field[(long long)b * HW + r] = (-90.0f + (float)bi * bin) + bin * 0.5f;
+  }
+}
+
 // Classification variant: argmax over channels + bin decode (gravity_head.py:243-244 + utils.py:114-130;
 // latitude_head.py:205-208 + utils.py:148-162).  logits NCHW [B, NC, HW] -> field [B, 2 or 1, HW].
 // torch.argmax returns the FIRST maximal index; strict '>' reproduces that.
@@ -635,18 +647,60 @@ __global__ void __launch_bounds__(256) argmax_decode_kernel(const float* __restr
     const float v = __ldg(lp + (long long)c * HW);
     if (v > best) { best = v; bi = c; }
   }
-  if (is_gravity) {
-    // angle = (bin * (360/(NC-1)) - 180) / 180 * pi ; bin NC-1 -> (0, 0).  torch evaluates this in fp32 on an int64
-    // tensor promoted to float: bin*5.0 - 180 exact in fp32, then /180*pi.
-    float* o = field + (long long)b * 2 * HW + r;
-    if (bi == NC - 1) { o[0] = 0.f; o[HW] = 0.f; }
-    else {
-      const float ang = ((float)bi * (360.0f / (float)(NC - 1)) - 180.0f) / 180.0f * 3.14159265358979323846f;
-      o[0] = cosf(ang); o[HW] = sinf(ang);
+  decode_bin_store(field, b, r, HW, NC, bi, is_gravity);
+}
+
+// Classification heads WITHOUT the logits (option "decode_only"): 1x1 prediction conv 32 -> NC
+// (gravity_head.py:175 / latitude_head.py:174), argmax over the NC logits and bin decode in one pass; the 73 / 180-channel
+// logit tensors (103.6 MB per image) are never written.  Four lanes (a quad) share one pixel: lane q evaluates the classes
+// c = q, q + 4, ... with the SAME fma chain as pred_tail_kernel (bias first, then channels 0..31 in order: bit-identical logits,
+// hence the same argmax as the default path), keeps its first maximum, and the quad's winner is found with two warp shuffles
+// (larger logit wins, the lower class index on ties = torch.argmax's first maximal index).
+// in: [npix, ldi] NHWC (32 channels at icoff); weights [NC][32] + bias staged in shared memory with rows padded to 36 floats
+// (the four lanes of a quad read four different rows with 16-byte loads: no bank conflict).
+__global__ void __launch_bounds__(256) pred_argmax_decode_kernel(const float* __restrict__ in, int ldi, int icoff, const float* __restrict__ w,
+                                                                 const float* __restrict__ bias, float* __restrict__ field, int B, int HW, int NC,
+                                                                 int is_gravity) {
+  extern __shared__ __align__(16) float s_pw[];  // [NC][36] then [NC]
+  for (int i = threadIdx.x; i < NC * 32; i += blockDim.x) s_pw[(i >> 5) * 36 + (i & 31)] = __ldg(w + i);
+  float* s_b = s_pw + NC * 36;
+  for (int i = threadIdx.x; i < NC; i += blockDim.x) s_b[i] = __ldg(bias + i);
+  __syncthreads();
+  const int q = threadIdx.x & 3;
+  const long long npix = (long long)B * HW;
+  const long long stride = (long long)gridDim.x * (blockDim.x >> 2);
+  const long long pix_last = npix - 1;
+  // (every lane of a warp runs the same number of iterations: the shuffles below need the full quad)
+  const long long iters = (npix + stride - 1) / stride;
+  long long pix = (long long)blockIdx.x * (blockDim.x >> 2) + (threadIdx.x >> 2);
+  for (long long it = 0; it < iters; ++it, pix += stride) {
+    const bool live = pix <= pix_last;
+    const long long pc = live ? pix : pix_last;
+    float f[32];
+#pragma unroll
+    for (int d = 0; d < 32; d += 4) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(in + pc * ldi + icoff + d));
+      f[d] = t.x; f[d + 1] = t.y; f[d + 2] = t.z; f[d + 3] = t.w;
     }
-  } else {
-    const float bin = 180.0f / (float)NC;
-    field[(long long)b * HW + r] = (-90.0f + (float)bi * bin) + bin * 0.5f;
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int c = q; c < NC; c += 4) {
+      const float4* wr = reinterpret_cast<const float4*>(s_pw + c * 36);
+      float v = s_b[c];
+#pragma unroll
+      for (int d4 = 0; d4 < 8; ++d4) {
+        const float4 ww = wr[d4];
+        v = fmaf(f[4 * d4], ww.x, v); v = fmaf(f[4 * d4 + 1], ww.y, v); v = fmaf(f[4 * d4 + 2], ww.z, v); v = fmaf(f[4 * d4 + 3], ww.w, v);
+      }
+      if (v > best || bi == 0x7fffffff) { best = v; bi = c; }      // strict '>': first maximal index of this lane's classes
+    }
+#pragma unroll
+    for (int o = 1; o < 4; o <<= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (live && q == 0) decode_bin_store(field, (int)(pix / HW), (int)(pix % HW), HW, NC, bi, is_gravity);
   }
 }
 

@@ -4,6 +4,7 @@
 #include "../../include/pf_b200.h"
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <atomic>
 #include <cctype>
@@ -13,19 +14,19 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <functional>
 #include <unordered_map>
 #include <vector>
 
 #include "common.cuh"
-#include "conv_gemm.cuh"
-#include "conv_gemm_tc.cuh"
-#include "conv3x3_tc.cuh"
 #include "tma_host.cuh"
 #include "attention_mma.cuh"
 #include "layers.cuh"
 #include "prepost.cuh"
+#include "comm.cuh"
+#include "jpeg.cuh"
 
 using namespace pf;
 
@@ -57,6 +58,8 @@ static bool sync_debug() {
 }
 // pf_profile_kernels_*: a CUDA-event pair around EVERY launch of the forward graph (in-pipeline time per kernel, bench.py's
 // "per_kernel" table).  Off by default: the event records cost a few percent, so bench.py uses a separate pass for it.
+// The state lives in the engine; the launch macro reaches it through a thread-local pointer that pf_forward sets for the
+// duration of the call (operator entry points run with it unset).
 struct KernelProf {
   bool on = false;
   cudaStream_t st = nullptr;
@@ -66,20 +69,26 @@ struct KernelProf {
   std::vector<Rec> recs;
   cudaEvent_t next() { return used < pool.size() ? pool[used++] : nullptr; }
 };
-static KernelProf g_kp;
+static thread_local KernelProf* tl_kp = nullptr;
 #define LAUNCHED(expr)                                                                              \
   do {                                                                                              \
-    cudaEvent_t ka__ = g_kp.on ? g_kp.next() : nullptr;                                             \
-    if (ka__) cudaEventRecord(ka__, g_kp.st);                                                       \
+    KernelProf* kp__ = tl_kp;                                                                       \
+    cudaEvent_t ka__ = (kp__ && kp__->on) ? kp__->next() : nullptr;                                 \
+    if (ka__) cudaEventRecord(ka__, kp__->st);                                                      \
     cudaError_t e__ = (expr);                                                                       \
     g_launches.fetch_add(1, std::memory_order_relaxed);                                             \
     if (ka__) {                                                                                     \
-      cudaEvent_t kb__ = g_kp.next();                                                               \
-      if (kb__) { cudaEventRecord(kb__, g_kp.st); g_kp.recs.push_back({#expr, ka__, kb__}); }       \
+      cudaEvent_t kb__ = kp__->next();                                                              \
+      if (kb__) { cudaEventRecord(kb__, kp__->st); kp__->recs.push_back({#expr, ka__, kb__}); }     \
     }                                                                                               \
     if (e__ == cudaSuccess && sync_debug()) e__ = cudaDeviceSynchronize();                          \
     if (e__ != cudaSuccess) return fail(PF_ERR_CUDA, "%s: %s (%s:%d, after tap '%s')", #expr, cudaGetErrorString(e__), __FILE__, __LINE__, g_crumb); \
   } while (0)
+// NVTX range per section of the forward graph (visible in Nsight Systems / ncu --nvtx; a few ns when no tool is attached)
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 #define TRY(expr)                \
   do {                           \
     int r__ = (expr);            \
@@ -134,6 +143,7 @@ struct pf_engine {
   GemmW conv0, conv1;
   GemmW conv1p;                       // conv_fuse_conv1 composed with the x2 upsample in front of it: 4 phases x 32 outputs per head
   const float *conv1f_w, *conv1f_b;   // plain fp32 conv_fuse_conv1 [head][tap][ci][o] / bias, for the border-ring kernel
+  bool decode_only = false;           // option "decode_only": classification heads return decoded fields, logits are never written
   bool use_attn_split = true;         // option "attn_split": q / kv leave their GEMMs as split planes (0 = fp32, split inside the attention kernel)
   bool use_phase = true;              // option "phase_conv1": 0 = materialise the upsampled tensor and run conv1 at 320x320
   const float *pred_g_w, *pred_g_b, *pred_l_w, *pred_l_b;
@@ -142,9 +152,15 @@ struct pf_engine {
   GemmW pn_ds[4];
   std::vector<CnxBlockW> pn_blocks[4];
   const float *pn_head_w, *pn_head_b;
-  // Pillow resample tables, cached per input size (device memory owned by the engine)
+  // Pillow resample tables, cached per input size in one device slab owned by the engine (bump allocation; built on the host
+  // into a pinned mirror of the slab and copied with cudaMemcpyAsync on the caller's stream: no allocation and no
+  // synchronising copy inside pf_forward)
   struct DevTable { int ksize; int* bounds; int* coeffs; };
   std::map<int, DevTable> tables;
+  char* table_dev = nullptr;
+  char* table_host = nullptr;       // pinned
+  long long table_off = 0;
+  KernelProf kp;                    // pf_profile_kernels_*
   // per-launch profiling of the GEMM engine (bench.py roofline leg): CUDA events on the launch stream
   // tensor maps are pure functions of (pointer, shape, box): cached across calls (the arena hands out the same addresses for the
   // same batch size), which takes cuTensorMapEncodeTiled (~5 us each, ~1800 per forward) off the launch path
@@ -162,10 +178,7 @@ struct pf_engine {
   std::unordered_map<MapKey, CUtensorMap, MapKeyHash> map_cache;
   bool use_stem_tc = true;    // 7x7 stems as patch gather + TMA GEMM (option "stem_tc"; 0 = fp32 CUDA-core direct convolution)
   bool use_attn_mma = true;   // tensor-core attention core (option "attn_mma"; 0 = CUDA-core fp32 kernel)
-  bool use_tma = true;   // whole forward on the TMA -> tcgen05 engine with pre-split activations (option "tma"; 0 = legacy engines)
   int sm_count = 148;
-  bool use_halo = true;  // 3x3/s1/p1 convolutions on the halo-tile tcgen05 kernel (option "halo3x3")
-  bool use_tc = true;    // route every eligible GEMM to the tcgen05/TMEM engine (option "tcgen05" = 0: HMMA engine)
   bool profile = false;
   struct ProfRec { cudaEvent_t a, b; double flops; int cfg; int M, N, K, KH, stride, groups, Cin; };
   std::vector<ProfRec> prof;
@@ -318,51 +331,6 @@ struct Fwd {
     vsnprintf(buf, sizeof buf, fmt, ap);
     va_end(ap);
     return tap(buf, p, numel);
-  }
-
-  // generic conv-as-GEMM launch; fills the common fields
-  int gemm(ConvGemmParams p) {
-    if (dry) return PF_OK;
-    const char* msg = conv_gemm_check(p);
-    if (msg) return fail(PF_ERR_ARG, "%s", msg);
-    const bool tc = e->use_tc && conv_gemm_tc_eligible(p);
-    const bool halo = tc && e->use_halo && conv3x3_tc_eligible(p);
-    auto launch = [&]() { return halo ? conv3x3_tc_launch(p, st) : (tc ? conv_gemm_tc_launch(p, st) : conv_gemm_launch(p, st)); };
-    if (e->profile) {
-      pf_engine::ProfRec r{};
-      for (cudaEvent_t* ev : {&r.a, &r.b}) {
-        if (e->ev_pool.empty()) { CU(cudaEventCreate(ev)); }
-        else { *ev = e->ev_pool.back(); e->ev_pool.pop_back(); }
-      }
-      r.flops = 2.0 * (double)p.B * p.OH * p.OW * (double)p.N * (double)p.K * (double)p.groups;
-      r.cfg = halo ? 4 : (tc ? 3 : conv_gemm_config(p));
-      r.M = p.B * p.OH * p.OW; r.N = p.N; r.K = p.K; r.KH = p.KH; r.stride = p.stride; r.groups = p.groups; r.Cin = p.Cin;
-      CU(cudaEventRecord(r.a, st));
-      LAUNCHED(launch());
-      CU(cudaEventRecord(r.b, st));
-      e->prof.push_back(r);
-      return PF_OK;
-    }
-    LAUNCHED(launch());
-    return PF_OK;
-  }
-  static ConvGemmParams base(const float* A, int lda, int B, int H, int W, int Cin, int KH, int stride, int pad, const GemmW& w, int N,
-                             float* C, int ldc) {
-    ConvGemmParams p{};
-    p.A = A; p.lda = lda; p.B = B; p.H = H; p.W = W; p.Cin = Cin;
-    p.KH = p.KW = KH; p.stride = stride; p.pad = pad;
-    p.OH = (H + 2 * pad - KH) / stride + 1; p.OW = (W + 2 * pad - KH) / stride + 1;
-    p.Whi = w.hi; p.Wlo = w.lo; p.N = N; p.K = KH * KH * Cin;
-    p.bias = w.b; p.bias_mode = w.b ? 1 : 0;
-    p.C = C; p.ldc = ldc; p.groups = 1;
-    return p;
-  }
-  // y[rows, N] = x[rows, K] W^T + b (+res)
-  int linear(const float* x, long long rows, int K, const GemmW& w, int N, float* y, int act = 0, const float* res = nullptr,
-             const float* gamma = nullptr) {
-    ConvGemmParams p = base(x, K, (int)rows, 1, 1, K, 1, 1, 0, w, N, y, N);  // rows as the batch dim: no spatial limit
-    p.act = act; p.res = res; p.ldr = N; p.gamma = gamma;
-    return gemm(p);
   }
 
   // ------------------------------------------------------------------------------------------ TMA engine helpers
@@ -531,16 +499,30 @@ struct Fwd {
 };
 
 // ----------------------------------------------------------------------------------------------- the forward graph
-static int get_table(pf_engine* e, int in_size, pf_engine::DevTable* out) {
+constexpr long long kTableSlabBytes = 8LL << 20;   // ~370 tables of a 2048-pixel axis; reset (after a stream sync) when full
+static int get_table(pf_engine* e, int in_size, pf_engine::DevTable* out, cudaStream_t st) {
   auto it = e->tables.find(in_size);
   if (it == e->tables.end()) {
     ResampleTable t = make_resample_table(in_size, kNet);
+    const long long nb = (long long)t.bounds.size() * sizeof(int), nc = (long long)t.coeffs.size() * sizeof(int);
+    const long long need = ((nb + 255) & ~255LL) + ((nc + 255) & ~255LL);
+    if (need > kTableSlabBytes) return fail(PF_ERR_ARG, "image axis of %d pixels is too long for the resize tables", in_size);
+    if (e->table_off + need > kTableSlabBytes) {
+      // slab full: earlier forwards on this stream may still read the old tables and the pinned mirror may still be the source
+      // of an in-flight copy -> drain the stream once, then start over
+      CU(cudaStreamSynchronize(st));
+      e->tables.clear();
+      e->table_off = 0;
+    }
     pf_engine::DevTable d{};
     d.ksize = t.ksize;
-    CU(cudaMalloc(&d.bounds, t.bounds.size() * sizeof(int)));
-    CU(cudaMalloc(&d.coeffs, t.coeffs.size() * sizeof(int)));
-    CU(cudaMemcpy(d.bounds, t.bounds.data(), t.bounds.size() * sizeof(int), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(d.coeffs, t.coeffs.data(), t.coeffs.size() * sizeof(int), cudaMemcpyHostToDevice));
+    const long long o0 = e->table_off, o1 = o0 + ((nb + 255) & ~255LL);
+    memcpy(e->table_host + o0, t.bounds.data(), nb);
+    memcpy(e->table_host + o1, t.coeffs.data(), nc);
+    d.bounds = (int*)(e->table_dev + o0);
+    d.coeffs = (int*)(e->table_dev + o1);
+    CU(cudaMemcpyAsync(e->table_dev + o0, e->table_host + o0, need, cudaMemcpyHostToDevice, st));
+    e->table_off += need;
     it = e->tables.emplace(in_size, d).first;
   }
   *out = it->second;
@@ -575,8 +557,8 @@ static int fwd_preprocess(Fwd& F, const pf_batch* bt, float*& x0, PreImage*& d_p
         const int H = bt->height[i], W = bt->width[i];
         if (H < 1 || W < 1) return fail(PF_ERR_ARG, "image %d has size %dx%d", i, H, W);
         pf_engine::DevTable tx, ty;
-        TRY(get_table(e, W, &tx));
-        TRY(get_table(e, H, &ty));
+        TRY(get_table(e, W, &tx, st));
+        TRY(get_table(e, H, &ty, st));
         if (ty.ksize + 1 > kPreMaxSmemRows) return fail(PF_ERR_ARG, "image %d is too tall (%d rows) for the resize kernel", i, H);
         pre[i] = PreImage{bt->image_offset[i], H, W, tx.ksize, ty.ksize, tx.bounds, tx.coeffs, ty.bounds, ty.coeffs};
         if (H > max_h) max_h = H;
@@ -585,11 +567,6 @@ static int fwd_preprocess(Fwd& F, const pf_batch* bt, float*& x0, PreImage*& d_p
       int rows = pre_rows_needed(max_h);
       if (rows > kPreMaxSmemRows) rows = kPreMaxSmemRows;
       const int smem = rows * kNet * 3;
-      static int configured_smem = 0;
-      if (smem > configured_smem) {
-        CU(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem > 48 * 1024 ? smem : 48 * 1024));
-        configured_smem = smem;
-      }
       LAUNCHED((preprocess_kernel<<<dim3(kNet / kPreRows, n), kNet, smem, st>>>(bt->images_u8, d_pre, x0, D.pixel_mean[0], D.pixel_mean[1],
                                                                                D.pixel_mean[2], D.pixel_std[0], D.pixel_std[1], D.pixel_std[2], rows),
                 cudaGetLastError()));
@@ -603,6 +580,27 @@ static int fwd_preprocess(Fwd& F, const pf_batch* bt, float*& x0, PreImage*& d_p
   return PF_OK;
 }
 
+// resample of the (decoded) 320x320 fields to the original sizes: one launch for all images of the batch
+static int launch_postprocess(const float* vec, const float* lat, int n, const int32_t* height, const int32_t* width, const int64_t* g_off,
+                              const int64_t* l_off, float* g_out, float* l_out, int lat_is_sin, PostImage* d_post, cudaStream_t st) {
+  std::vector<PostImage> post(n);
+  long long total = 0;
+  int max_h = 1, max_wp = 4;
+  for (int i = 0; i < n; ++i) {
+    if (height[i] < 1 || width[i] < 1) return fail(PF_ERR_ARG, "image %d has size %dx%d", i, height[i], width[i]);
+    post[i] = PostImage{height[i], width[i], g_off[i], l_off[i], total};
+    total += (long long)height[i] * width[i];
+    if (height[i] > max_h) max_h = height[i];
+    const int wp = (width[i] + 3) / 4 * 4;
+    if (wp > max_wp) max_wp = wp;
+  }
+  CU(cudaMemcpyAsync(d_post, post.data(), n * sizeof(PostImage), cudaMemcpyHostToDevice, st));
+  const int smem = (max_wp <= kPostMaxW ? max_wp : 4) * 8;
+  LAUNCHED((postprocess_kernel<<<dim3((unsigned)cdiv(max_h, kPostBand), (unsigned)n), kPostThreads, smem, st>>>(vec, lat, d_post, g_out, l_out, lat_is_sin),
+            cudaGetLastError()));
+  return PF_OK;
+}
+
 // prediction 1x1 convs (+ normalise / clamp) -> NCHW outputs, then argmax decode (classification) and resample to the
 // original resolutions.  conv1_out: [n,320,320,64] fp32 (gravity head channels 0-31, latitude head 32-63).
 static int fwd_tails_post(Fwd& F, const pf_batch* bt, const float* conv1_out, PostImage* d_post, bool pred_done = false) {
@@ -612,228 +610,59 @@ static int fwd_tails_post(Fwd& F, const pf_batch* bt, const float* conv1_out, Po
   const bool dry = F.dry;
   cudaStream_t st = F.st;
   Arena& ar = F.ar;
-  // prediction tails -> NCHW outputs (returned to the caller)
   const int HW = kNet * kNet;
-  if (!dry && !pred_done) {
-    const unsigned grid = (unsigned)cdivl((long long)n * HW, 128);
-    LAUNCHED((pred_tail_kernel<<<grid, 128, D.gravity_classes * 33 * 4, st>>>(conv1_out, 64, 0, e->pred_g_w, e->pred_g_b, bt->pred_gravity, n, HW,
-                                                                           D.gravity_classes, D.gravity_classes == 2 ? 1 : 0), cudaGetLastError()));
-    LAUNCHED((pred_tail_kernel<<<grid, 128, D.latitude_classes * 33 * 4, st>>>(conv1_out, 64, 32, e->pred_l_w, e->pred_l_b, bt->pred_latitude, n, HW,
-                                                                            D.latitude_classes, D.latitude_classes == 1 ? 2 : 0), cudaGetLastError()));
-  }
-
-  // ---------------- post-process to the original resolutions ------------------------------------------------
+  const bool cls_g = D.gravity_classes != 2, cls_l = D.latitude_classes != 1;
+  const bool fused_decode = e->decode_only && (cls_g || cls_l);
+  if (e->decode_only && cls_g != cls_l) return fail(PF_ERR_ARG, "decode_only needs both heads to be classification heads");
   const float* vec = dry ? nullptr : bt->pred_gravity;
   const float* lat = dry ? nullptr : bt->pred_latitude;
-  const bool cls_g = D.gravity_classes != 2, cls_l = D.latitude_classes != 1;
-  if (cls_g) {
-    float* dv = ar.f((long long)n * 2 * HW);
-    if (!dry) LAUNCHED((argmax_decode_kernel<<<(unsigned)cdivl((long long)n * HW, 256), 256, 0, st>>>(bt->pred_gravity, dv, n, HW, D.gravity_classes, 1), cudaGetLastError()));
-    vec = dv;
-  }
-  if (cls_l) {
-    float* dl = ar.f((long long)n * HW);
-    if (!dry) LAUNCHED((argmax_decode_kernel<<<(unsigned)cdivl((long long)n * HW, 256), 256, 0, st>>>(bt->pred_latitude, dl, n, HW, D.latitude_classes, 0), cudaGetLastError()));
-    lat = dl;
-  }
-  if (!dry) {
-    std::vector<PostImage> post(n);
-    long long total = 0, max_quads = 1;
-    for (int i = 0; i < n; ++i) {
-      post[i] = PostImage{bt->height[i], bt->width[i], bt->gravity_original_offset[i], bt->latitude_original_offset[i], total};
-      total += (long long)bt->height[i] * bt->width[i];
-      const long long quads = (long long)bt->height[i] * ((bt->width[i] + 3) / 4);
-      if (quads > max_quads) max_quads = quads;
-    }
-    CU(cudaMemcpyAsync(d_post, post.data(), n * sizeof(PostImage), cudaMemcpyHostToDevice, st));
-    LAUNCHED((postprocess_kernel<<<dim3((unsigned)cdivl(max_quads, 256), (unsigned)n), 256, 0, st>>>(vec, lat, d_post, n, total, bt->gravity_original,
-                                                                                                     bt->latitude_original, cls_l ? 0 : 1), cudaGetLastError()));
-  }
-
-  return PF_OK;
-}
-
-static int run_forward(Fwd& F, const pf_batch* bt, int max_h_for_dry) {
-  pf_engine* e = F.e;
-  const pf_model_desc& D = e->desc;
-  const int n = F.n;
-  const bool dry = F.dry;
-  cudaStream_t st = F.st;
-  Arena& ar = F.ar;
-
-  float* x0; PreImage* d_pre; PostImage* d_post;
-  TRY(fwd_preprocess(F, bt, x0, d_pre, d_post));
-  TRY(F.tap("pre", x0, (long long)n * kNet * kNet * 4));
-
-  // ---------------- persistent feature maps ---------------------------------------------------------------
-  float* cfeat[4];
-  for (int s = 0; s < 4; ++s) cfeat[s] = ar.f((long long)n * kMitRes[s] * kMitRes[s] * kMitDims[s]);
-  float* ll = ar.f((long long)n * 160 * 160 * 64);
-  if (!dry) LAUNCHED((stem_conv_launch<7, 7, 2, 3, 64>(x0, 4, n, kNet, kNet, e->llenc_w, e->llenc_b, ll, 1, st)));
-  TRY(F.tap("ll", ll, (long long)n * 160 * 160 * 64));
-
-  // ---------------- MiT-B3 encoder (mix_transformers.py:449-485) -------------------------------------------
-  for (int s = 0; s < 4; ++s) {
-    const int C = kMitDims[s], R = kMitRes[s], N = R * R, heads = kMitHeads[s], sr = kMitSr[s];
-    const long long rows = (long long)n * N;
-    const long long m = ar.mark();
-    float* x = ar.f(rows * C);
-    float* t1 = ar.f(rows * C);
-    float* q = ar.f(rows * C);
-    float* a = ar.f(rows * C);
-    float* t2 = ar.f((long long)n * 100 * C);
-    float* kv = ar.f((long long)n * 100 * 2 * C);
-    float* h1 = ar.f(rows * 4 * C);
-    float* h2 = ar.f(rows * 4 * C);
-    // OverlapPatchEmbed: conv + LayerNorm(eps 1e-5)
-    if (s == 0) {
-      if (!dry) LAUNCHED((stem_conv_launch<7, 7, 4, 3, 64>(x0, 4, n, kNet, kNet, e->embed1_w, e->embed1_b, t1, 0, st)));
-    } else {
-      ConvGemmParams p = Fwd::base(cfeat[s - 1], kMitDims[s - 1], n, kMitRes[s - 1], kMitRes[s - 1], kMitDims[s - 1], 3, 2, 1, e->embed[s], C, t1, C);
-      TRY(F.gemm(p));
-    }
-    TRY(F.ln(t1, x, rows, C, e->embed_ln[s], 1e-5f));
-    TRY(F.tapf(x, rows * C, "mit.s%d.embed", s + 1));
-    for (int i = 0; i < kMitDepths[s]; ++i) {
-      const MitBlockW& b = e->blocks[s][i];
-      // x = x + attn(norm1(x))
-      TRY(F.ln(x, t1, rows, C, b.ln1, 1e-6f));
-      TRY(F.linear(t1, rows, C, b.q, C, q));
-      if (sr > 1) {
-        ConvGemmParams p = Fwd::base(t1, C, n, R, R, C, sr, sr, 0, b.sr, C, t2, C);
-        TRY(F.gemm(p));
-        TRY(F.ln(t2, t2, (long long)n * 100, C, b.srln, 1e-5f));
-        TRY(F.linear(t2, (long long)n * 100, C, b.kv, 2 * C, kv));
-      } else {
-        TRY(F.linear(t1, rows, C, b.kv, 2 * C, kv));
-      }
-      if (!dry) LAUNCHED(attention_launch(q, kv, a, n, N, C, heads, st));
-      TRY(F.linear(a, rows, C, b.proj, C, x, 0, x));
-      TRY(F.tapf(x, rows * C, "mit.s%d.b%d.attn", s + 1, i));
-      // x = x + mlp(norm2(x))
-      TRY(F.ln(x, t1, rows, C, b.ln2, 1e-6f));
-      TRY(F.linear(t1, rows, C, b.fc1, 4 * C, h1));
-      if (!dry) LAUNCHED((dwconv3x3_gelu_kernel<<<ew_grid((long long)n * ((R + 1) / 2) * ((R + 3) / 4) * C), 256, 0, st>>>(h1, h2, n, R, R, 4 * C, b.dw_w, b.dw_b), cudaGetLastError()));
-      TRY(F.linear(h2, rows, 4 * C, b.fc2, C, x, 0, x));
-      TRY(F.tapf(x, rows * C, "mit.s%d.b%d", s + 1, i));
-    }
-    TRY(F.ln(x, cfeat[s], rows, C, e->stage_norm[s], 1e-6f));
-    TRY(F.tapf(cfeat[s], rows * C, "mit.c%d", s + 1));
-    ar.release(m);
-  }
-
-  // ---------------- decoder heads, gravity (group 0) and latitude (group 1) side by side -------------------
-  // Tensors carry both heads in the channel dimension: [n, h, w, 2*C], head g = channels [g*C, (g+1)*C).
-  float* conv1_out = ar.f((long long)n * kNet * kNet * 64);
-  {
-    const long long m = ar.mark();
-    float* fused = nullptr;  // running top-down feature, [n, r, r, 512] at the resolution of the next level
-    for (int lvl = 4; lvl >= 1; --lvl) {
-      const int r = kMitRes[lvl - 1], Cin = kMitDims[lvl - 1];
-      const long long px = (long long)n * r * r;
-      float* t = ar.f(px * 512);   // linear_c{lvl} o linear_c{lvl}_proc, composed (exact; bias via border classes)
-      float* u = ar.f(px * 512);
-      float* v = ar.f(px * 512);
-      {
-        ConvGemmParams p = Fwd::base(cfeat[lvl - 1], Cin, n, r, r, Cin, 3, 1, 1, e->proc[lvl - 1], 512, t, 512);
-        p.bias_mode = 2;
-        TRY(F.gemm(p));
-        TRY(F.tapf(t, px * 512, "head.proc%d", lvl));
-      }
-      auto rcu_conv = [&](const float* A, const GemmW& w, float* Cout, int act, const float* res, int res_relu, const float* res2) {
-        ConvGemmParams p = Fwd::base(A, 512, n, r, r, 256, 3, 1, 1, w, 256, Cout, 512);
-        p.in_relu = (act == 1);  // conv1 of a unit reads relu(x); conv2 reads conv1's (already rectified) output
-        p.act = act;
-        p.res = res; p.ldr = 512; p.res_relu = res_relu;
-        p.res2 = res2; p.ldr2 = 512;
-        p.groups = 2; p.a_gcoff = 256; p.c_gcoff = 256; p.r_gcoff = 256; p.r2_gcoff = 256;
-        p.w_gstride = 256LL * 2304; p.bias_gstride = 256;
-        return F.gemm(p);
-      };
-      const float* o = t;
-      if (lvl < 4) {
-        // output = xs[0] + resConfUnit1(xs[1]);  RCU(x) = conv2(relu(conv1(relu(x)))) + relu(x)   (decode_head.py:244-282)
-        TRY(rcu_conv(t, e->rcu[lvl - 1][0][0], u, 1, nullptr, 0, nullptr));
-        TRY(rcu_conv(u, e->rcu[lvl - 1][0][1], v, 0, t, 1, fused));
-        o = v;
-      }
-      float* w2 = ar.f(px * 512);
-      TRY(rcu_conv(o, e->rcu[lvl - 1][1][0], u, 1, nullptr, 0, nullptr));
-      TRY(rcu_conv(u, e->rcu[lvl - 1][1][1], w2, 0, o, 1, nullptr));
-      float* up = ar.f(px * 4 * 512);
-      if (!dry) LAUNCHED((upsample2x_kernel<<<ew_grid(px * 4 * 64), 256, 0, st>>>(w2, 512, 0, up, 512, 0, n, r, r, 512), cudaGetLastError()));
-      fused = up;
-      TRY(F.tapf(up, px * 4 * 512, "head.fusion%d", lvl));
-    }
-    // conv_fuse_conv0 on cat([fused, ll]) (gravity_head.py:170-171), both heads
-    float* c0 = ar.f((long long)n * 160 * 160 * 128);
-    {
-      ConvGemmParams p = Fwd::base(fused, 512, n, 160, 160, 320, 3, 1, 1, e->conv0, 64, c0, 128);
-      p.A2 = ll; p.lda2 = 64; p.a2_coff = 0; p.c_split = 256;
-      p.act = 1;
-      p.groups = 2; p.a_gcoff = 256; p.c_gcoff = 64; p.w_gstride = 64LL * 2880; p.bias_gstride = 64;
-      TRY(F.gemm(p));
-      TRY(F.tap("head.conv0", c0, (long long)n * 160 * 160 * 128));
-    }
-    float* c0u = ar.f((long long)n * kNet * kNet * 128);
-    if (!dry) LAUNCHED((upsample2x_kernel<<<ew_grid((long long)n * kNet * kNet * 16), 256, 0, st>>>(c0, 128, 0, c0u, 128, 0, n, 160, 160, 128), cudaGetLastError()));
-    {
-      ConvGemmParams p = Fwd::base(c0u, 128, n, kNet, kNet, 64, 3, 1, 1, e->conv1, 32, conv1_out, 64);
-      p.act = 1;
-      p.groups = 2; p.a_gcoff = 64; p.c_gcoff = 32; p.w_gstride = 32LL * 576; p.bias_gstride = 32;
-      TRY(F.gemm(p));
-      TRY(F.tap("head.conv1", conv1_out, (long long)n * kNet * kNet * 64));
-    }
-    ar.release(m);
-  }
-  TRY(fwd_tails_post(F, bt, conv1_out, d_post));
-  const int HW = kNet * kNet;
-  const bool cls_g = D.gravity_classes != 2, cls_l = D.latitude_classes != 1;
-  (void)HW;
-
-  // ---------------- ParamNet (ConvNeXt-T on the predicted fields) -------------------------------------------
-  if (D.param_net != PF_PARAM_NONE) {
-    if (cls_g || cls_l) return fail(PF_ERR_ARG, "ParamNet needs regression heads");
-    const int S = D.param_net == PF_PARAM_CENTERED ? kNet : D.param_input_size;
-    float* pin = ar.f((long long)n * S * S * 4);
-    if (!dry) LAUNCHED((pack_fields_kernel<<<(unsigned)cdivl((long long)n * S * S, 256), 256, 0, st>>>(bt->pred_gravity, bt->pred_latitude, pin, n, S), cudaGetLastError()));
-    int r = S / 4;
-    float* x = ar.f((long long)n * r * r * 96);
-    if (!dry) LAUNCHED((stem_conv_launch<4, 4, 4, 0, 96>(pin, 4, n, S, S, e->pn_stem_w, e->pn_stem_b, x, 0, st)));
-    TRY(F.ln(x, x, (long long)n * r * r, 96, e->pn_stem_ln, 1e-6f));
-    for (int s = 0; s < 4; ++s) {
-      const int C = kCnxDims[s];
-      if (s > 0) {
-        // downsample: LayerNorm (channels_first == per-pixel LN in NHWC) + conv2x2/2 (convnext.py:93-99)
-        const int r2 = r / 2;
-        float* y = ar.f((long long)n * r * r * kCnxDims[s - 1]);
-        TRY(F.ln(x, y, (long long)n * r * r, kCnxDims[s - 1], e->pn_ds_ln[s], 1e-6f));
-        float* xn = ar.f((long long)n * r2 * r2 * C);
-        ConvGemmParams p = Fwd::base(y, kCnxDims[s - 1], n, r, r, kCnxDims[s - 1], 2, 2, 0, e->pn_ds[s], C, xn, C);
-        TRY(F.gemm(p));
-        x = xn; r = r2;
-      }
-      const long long rows = (long long)n * r * r;
-      float* y = ar.f(rows * C);
-      float* h = ar.f(rows * 4 * C);
-      for (int j = 0; j < kCnxDepths[s]; ++j) {
-        const CnxBlockW& b = e->pn_blocks[s][j];
-        if (!dry) LAUNCHED((dwconv7x7_kernel<<<ew_grid((long long)n * ((r + 1) / 2) * ((r + 7) / 8) * (C / 4)), 256, 0, st>>>(x, y, n, r, r, C, b.dw_w, b.dw_b), cudaGetLastError()));
-        TRY(F.ln(y, y, rows, C, b.ln, 1e-6f));
-        TRY(F.linear(y, rows, C, b.pw1, 4 * C, h, 2));
-        TRY(F.linear(h, rows, 4 * C, b.pw2, C, x, 0, x, b.gamma));
-      }
-      TRY(F.tapf(x, rows * C, "cnx.s%d", s));
-    }
+  if (e->debug) {
+    // debug taps: the raw prediction-conv outputs before normalise / clamp (oracle taps g.raw / l.raw)
+    float* rg = ar.f((long long)n * D.gravity_classes * HW);
+    float* rl = ar.f((long long)n * D.latitude_classes * HW);
     if (!dry) {
-      if (!bt->params) return fail(PF_ERR_ARG, "params output is NULL");
-      LAUNCHED((param_tail_kernel<<<n, 256, 0, st>>>(x, r * r, e->pn_norm.w, e->pn_norm.b, e->pn_head_w, e->pn_head_b, bt->params, D.param_net), cudaGetLastError()));
+      const unsigned grid = (unsigned)cdivl((long long)n * HW, 128);
+      LAUNCHED((pred_tail_kernel<<<grid, 128, D.gravity_classes * 33 * 4, st>>>(conv1_out, 64, 0, e->pred_g_w, e->pred_g_b, rg, n, HW, D.gravity_classes, 0), cudaGetLastError()));
+      LAUNCHED((pred_tail_kernel<<<grid, 128, D.latitude_classes * 33 * 4, st>>>(conv1_out, 64, 32, e->pred_l_w, e->pred_l_b, rl, n, HW, D.latitude_classes, 0), cudaGetLastError()));
+    }
+    TRY(F.tap("head.raw_g", rg, (long long)n * D.gravity_classes * HW));
+    TRY(F.tap("head.raw_l", rl, (long long)n * D.latitude_classes * HW));
+  }
+  if (fused_decode) {
+    // option "decode_only": 1x1 conv + argmax + bin decode in one kernel; pred_gravity / pred_latitude hold the decoded fields
+    if (!dry) {
+      const unsigned grid = ew_grid((long long)n * HW * 4);
+      LAUNCHED((pred_argmax_decode_kernel<<<grid, 256, D.gravity_classes * 37 * 4, st>>>(conv1_out, 64, 0, e->pred_g_w, e->pred_g_b, bt->pred_gravity, n, HW,
+                                                                                      D.gravity_classes, 1), cudaGetLastError()));
+      LAUNCHED((pred_argmax_decode_kernel<<<grid, 256, D.latitude_classes * 37 * 4, st>>>(conv1_out, 64, 32, e->pred_l_w, e->pred_l_b, bt->pred_latitude, n, HW,
+                                                                                       D.latitude_classes, 0), cudaGetLastError()));
+    }
+  } else {
+    // prediction tails -> NCHW outputs (returned to the caller)
+    if (!dry && !pred_done) {
+      const unsigned grid = (unsigned)cdivl((long long)n * HW, 128);
+      LAUNCHED((pred_tail_kernel<<<grid, 128, D.gravity_classes * 33 * 4, st>>>(conv1_out, 64, 0, e->pred_g_w, e->pred_g_b, bt->pred_gravity, n, HW,
+                                                                             D.gravity_classes, D.gravity_classes == 2 ? 1 : 0), cudaGetLastError()));
+      LAUNCHED((pred_tail_kernel<<<grid, 128, D.latitude_classes * 33 * 4, st>>>(conv1_out, 64, 32, e->pred_l_w, e->pred_l_b, bt->pred_latitude, n, HW,
+                                                                              D.latitude_classes, D.latitude_classes == 1 ? 2 : 0), cudaGetLastError()));
+    }
+    if (cls_g) {
+      float* dv = ar.f((long long)n * 2 * HW);
+      if (!dry) LAUNCHED((argmax_decode_kernel<<<(unsigned)cdivl((long long)n * HW, 256), 256, 0, st>>>(bt->pred_gravity, dv, n, HW, D.gravity_classes, 1), cudaGetLastError()));
+      vec = dv;
+    }
+    if (cls_l) {
+      float* dl = ar.f((long long)n * HW);
+      if (!dry) LAUNCHED((argmax_decode_kernel<<<(unsigned)cdivl((long long)n * HW, 256), 256, 0, st>>>(bt->pred_latitude, dl, n, HW, D.latitude_classes, 0), cudaGetLastError()));
+      lat = dl;
     }
   }
-  (void)max_h_for_dry;
+  // ---------------- post-process to the original resolutions ------------------------------------------------
+  if (!dry)
+    TRY(launch_postprocess(vec, lat, n, bt->height, bt->width, bt->gravity_original_offset, bt->latitude_original_offset, bt->gravity_original,
+                           bt->latitude_original, cls_l ? 0 : 1, d_post, st));
   return PF_OK;
 }
-
 
 // =============================================================================================== TMA forward graph
 // Same network as run_forward, on the TMA -> tcgen05 engine: every GEMM input is a pre-split bf16 hi/lo tensor written by
@@ -848,9 +677,15 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
   using Epi = Fwd::Epi;
 
   float* x0; PreImage* d_pre; PostImage* d_post;
-  TRY(fwd_preprocess(F, bt, x0, d_pre, d_post));
+  {
+    NvtxRange r_("pf:preprocess");
+    TRY(fwd_preprocess(F, bt, x0, d_pre, d_post));
+  }
   TRY(F.tap("pre", x0, (long long)n * kNet * kNet * 4));
 
+  NvtxRange* sect = new NvtxRange("pf:ll_enc");
+  struct SectGuard { NvtxRange*& p; ~SectGuard() { delete p; } } sect_guard{sect};
+  auto section = [&](const char* name) { delete sect; sect = nullptr; sect = new NvtxRange(name); };
   SplitT cfeat[4];
   for (int s = 0; s < 4; ++s) cfeat[s] = F.salloc((long long)n * kMitRes[s] * kMitRes[s], kMitDims[s]);
   SplitT ll = F.salloc((long long)n * 160 * 160, 64);
@@ -869,6 +704,7 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
 
   // ---------------- MiT-B3 encoder ---------------------------------------------------------------------------
   for (int s = 0; s < 4; ++s) {
+    { char nm[32]; snprintf(nm, sizeof nm, "pf:mit.stage%d", s + 1); section(nm); }
     const int C = kMitDims[s], R = kMitRes[s], N = R * R, heads = kMitHeads[s], sr = kMitSr[s];
     const long long rows = (long long)n * N;
     const long long m = ar.mark();
@@ -939,6 +775,7 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
     float* fused = nullptr;       // fp32 top-down feature of the previous level, upsampled to this level's resolution
     SplitT fused_s;               // level 1 only: the final fused feature at 160x160, split (input of conv_fuse_conv0)
     for (int lvl = 4; lvl >= 1; --lvl) {
+      { char nm[32]; snprintf(nm, sizeof nm, "pf:heads.level%d", lvl); section(nm); }
       const int r = kMitRes[lvl - 1], Cin = kMitDims[lvl - 1];
       const long long px = (long long)n * r * r;
       float* t = ar.f(px * 512);
@@ -980,6 +817,7 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
     // conv_fuse_conv0 on cat([fused, ll]) -> ReLU ; x2 ; conv_fuse_conv1 -> ReLU
     // regression heads: the 1x1 prediction conv + normalise / clamp run inside conv_fuse_conv1's epilogue (conv1's own output is
     // then only materialised for the debug taps); classification heads (73 / 180 logits) keep the separate tail kernel
+    section("pf:heads.fuse_convs");
     fuse_pred = D.gravity_classes == 2 && D.latitude_classes == 1;
     const bool keep_conv1 = !fuse_pred || e->debug;   // (not `o.C != nullptr`: the sizing dry run has null pointers)
     PredTail pt[2] = {{e->pred_g_w, e->pred_g_b, dry ? nullptr : bt->pred_gravity, 2, 1}, {e->pred_l_w, e->pred_l_b, dry ? nullptr : bt->pred_latitude, 1, 2}};
@@ -996,11 +834,6 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
       if (keep_conv1) o.C = conv1_out;
       TRY(F.thalo(c0s, 0, 64, nullptr, 0, 0, n, 160, 160, 64, e->conv1p, 128, 2, 128, o, fuse_pred ? pt : nullptr));
       if (!dry) {
-        static bool ring_configured = false;
-        if (!ring_configured) {
-          CU(cudaFuncSetAttribute(conv1_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingSmem));
-          ring_configured = true;
-        }
         const dim3 grid((unsigned)cdiv(conv1_ring_count(kNet, kNet), kRingPx), (unsigned)n);
         LAUNCHED((conv1_ring_kernel<<<grid, 256, kRingSmem, st>>>(c0s.hi, c0s.lo, 160, 160, e->conv1f_w, e->conv1f_b, keep_conv1 ? conv1_out : nullptr,
                                                                  fuse_pred ? e->pred_g_w : nullptr, e->pred_g_b, bt->pred_gravity,
@@ -1022,10 +855,12 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
     if (keep_conv1) TRY(F.tap("head.conv1", conv1_out, (long long)n * kNet * kNet * 64));
     ar.release(m);
   }
+  section("pf:tails_postprocess");
   TRY(fwd_tails_post(F, bt, conv1_out, d_post, fuse_pred));
 
   // ---------------- ParamNet (ConvNeXt-T on the predicted fields) -------------------------------------------
   if (D.param_net != PF_PARAM_NONE) {
+    section("pf:paramnet");
     if (D.gravity_classes != 2 || D.latitude_classes != 1) return fail(PF_ERR_ARG, "ParamNet needs regression heads");
     const int S = D.param_net == PF_PARAM_CENTERED ? kNet : D.param_input_size;
     float* pin = ar.f((long long)n * S * S * 4);
@@ -1073,6 +908,28 @@ int pf_abi_version(void) { return PF_ABI_VERSION; }
 const char* pf_last_error(void) { return g_err.c_str(); }
 int64_t pf_kernel_launch_count(void) { return g_launches.load(); }
 
+// The opt-in for more than 48 KB of dynamic shared memory is a per-device attribute of each kernel: set for every kernel of the
+// library on every device an engine (or an operator entry point) uses, once per device and thread-safe.
+static int configure_device(int device) {
+  static std::mutex mu;
+  static std::vector<char> done;
+  std::lock_guard<std::mutex> lock(mu);
+  if (device < (int)done.size() && done[device]) return PF_OK;
+  CU(gemm_tma_configure_device());
+  CU(attention_mma_configure_device());
+  CU(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+  CU(cudaFuncSetAttribute(conv1_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingSmem));
+  CU(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPreMaxSmemRows * kNet * 3));
+  if (device >= (int)done.size()) done.resize(device + 1, 0);
+  done[device] = 1;
+  return PF_OK;
+}
+static int configure_current_device() {
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  return configure_device(dev);
+}
+
 int pf_create(int device, const pf_model_desc* desc, pf_handle* out) {
   if (!desc || !out) return fail(PF_ERR_ARG, "pf_create: null argument");
   if (!((desc->gravity_classes == 2 || desc->gravity_classes == 73) && (desc->latitude_classes == 1 || desc->latitude_classes == 180)))
@@ -1087,10 +944,17 @@ int pf_create(int device, const pf_model_desc* desc, pf_handle* out) {
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) return fail(PF_ERR_CUDA, "pf_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  TRY(configure_device(device));
   pf_engine* e = new pf_engine();
   e->device = device;
   e->sm_count = prop.multiProcessorCount;
   e->desc = *desc;
+  if (cudaMalloc(&e->table_dev, kTableSlabBytes) != cudaSuccess || cudaMallocHost(&e->table_host, kTableSlabBytes) != cudaSuccess) {
+    const int r = fail(PF_ERR_CUDA, "pf_create: resize-table slab: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(e->table_dev);
+    delete e;
+    return r;
+  }
   *out = e;
   return PF_OK;
 }
@@ -1098,9 +962,11 @@ int pf_create(int device, const pf_model_desc* desc, pf_handle* out) {
 int pf_destroy(pf_handle h) {
   if (!h) return PF_OK;
   cudaSetDevice(h->device);
-  for (auto& kv : h->tables) { cudaFree(kv.second.bounds); cudaFree(kv.second.coeffs); }
+  cudaFree(h->table_dev);
+  cudaFreeHost(h->table_host);
   for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto ev : h->ev_pool) cudaEventDestroy(ev);
+  for (auto ev : h->kp.pool) cudaEventDestroy(ev);
   delete h;
   return PF_OK;
 }
@@ -1125,7 +991,8 @@ int64_t pf_workspace_bytes(pf_handle h, int n, int max_h) {
   Fwd F{h, Arena{}, nullptr, true, n};
   F.ar.dry = true;
   F.ar.keep = h->debug;
-  int r = h->use_tma ? run_forward_tma(F, nullptr) : run_forward(F, nullptr, max_h);
+  (void)max_h;
+  int r = run_forward_tma(F, nullptr);
   if (r != PF_OK) return r;
   return F.ar.peak + 4096;
 }
@@ -1147,13 +1014,16 @@ int pf_forward(pf_handle h, const pf_batch* bt, void* workspace, int64_t workspa
   {  // capacity check with a dry run (cheap: no launches)
     Fwd T{h, Arena{}, nullptr, true, bt->n};
     T.ar.dry = true; T.ar.keep = h->debug;
-    TRY(h->use_tma ? run_forward_tma(T, nullptr) : run_forward(T, nullptr, 0));
+    TRY(run_forward_tma(T, nullptr));
     if (T.ar.peak > workspace_bytes) return fail(PF_ERR_WORKSPACE, "pf_forward: workspace %lld B < required %lld B", (long long)workspace_bytes, T.ar.peak);
   }
   if (((uintptr_t)workspace & 255) != 0) return fail(PF_ERR_ARG, "pf_forward: workspace must be 256-byte aligned");
   h->taps.clear();
-  g_kp.st = (cudaStream_t)stream;
-  return h->use_tma ? run_forward_tma(F, bt) : run_forward(F, bt, 0);
+  h->kp.st = (cudaStream_t)stream;
+  tl_kp = &h->kp;
+  const int r = run_forward_tma(F, bt);
+  tl_kp = nullptr;
+  return r;
 }
 
 int pf_profile_enable(pf_handle h, int on) {
@@ -1170,13 +1040,14 @@ int pf_profile_enable(pf_handle h, int on) {
 int pf_profile_kernels_enable(pf_handle h, int max_launches) {
   if (!h) return fail(PF_ERR_ARG, "null handle");
   CU(cudaSetDevice(h->device));
-  g_kp.on = max_launches > 0;
-  g_kp.used = 0;
-  g_kp.recs.clear();
-  while ((long long)g_kp.pool.size() < 2LL * max_launches) {
+  KernelProf& kp = h->kp;
+  kp.on = max_launches > 0;
+  kp.used = 0;
+  kp.recs.clear();
+  while ((long long)kp.pool.size() < 2LL * max_launches) {
     cudaEvent_t ev;
     CU(cudaEventCreate(&ev));
-    g_kp.pool.push_back(ev);
+    kp.pool.push_back(ev);
   }
   return PF_OK;
 }
@@ -1186,7 +1057,7 @@ int pf_profile_kernels_read(pf_handle h, char* buf, int cap) {
   if (!h || !buf || cap < 1) return fail(PF_ERR_ARG, "pf_profile_kernels_read: bad argument");
   std::map<std::string, std::pair<int, double>> agg;
   std::vector<std::string> order;
-  for (const auto& r : g_kp.recs) {
+  for (const auto& r : h->kp.recs) {
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, r.a, r.b));
     const char* c = r.expr;
@@ -1209,19 +1080,17 @@ int pf_profile_kernels_read(pf_handle h, char* buf, int cap) {
   }
   if ((int)out.size() + 1 > cap) return fail(PF_ERR_ARG, "pf_profile_kernels_read: buffer too small (%d needed)", (int)out.size() + 1);
   memcpy(buf, out.c_str(), out.size() + 1);
-  g_kp.used = 0;
-  g_kp.recs.clear();
+  h->kp.used = 0;
+  h->kp.recs.clear();
   return (int)out.size();
 }
 int pf_set_option(pf_handle h, const char* name, int value) {
   if (!h || !name) return fail(PF_ERR_ARG, "pf_set_option: null argument");
-  if (!strcmp(name, "tcgen05")) { h->use_tc = value != 0; return PF_OK; }
-  if (!strcmp(name, "halo3x3")) { h->use_halo = value != 0; return PF_OK; }
-  if (!strcmp(name, "tma")) { h->use_tma = value != 0; return PF_OK; }
   if (!strcmp(name, "attn_mma")) { h->use_attn_mma = value != 0; return PF_OK; }
   if (!strcmp(name, "stem_tc")) { h->use_stem_tc = value != 0; return PF_OK; }
   if (!strcmp(name, "phase_conv1")) { h->use_phase = value != 0; return PF_OK; }
   if (!strcmp(name, "attn_split")) { h->use_attn_split = value != 0; return PF_OK; }
+  if (!strcmp(name, "decode_only")) { h->decode_only = value != 0; return PF_OK; }
   return fail(PF_ERR_ARG, "pf_set_option: unknown option '%s'", name);
 }
 // out[cfg*3 + {0,1,2}] = {milliseconds, algorithmic FLOPs, launches} per GEMM engine configuration (7 configs),
@@ -1274,64 +1143,181 @@ int pf_debug_copy(pf_handle h, const char* name, float* dst, int64_t numel, void
   return fail(PF_ERR_ARG, "pf_debug_copy: no tap '%s'", name);
 }
 
+// ---- multi-GPU gather (NCCL point-to-point) ---------------------------------------------------
+#define NCCL_TRY(expr)                                                                                              \
+  do {                                                                                                              \
+    int r__ = (expr);                                                                                               \
+    if (r__ != kNcclSuccess) return fail(PF_ERR_CUDA, "%s: %s", #expr, api.GetErrorString ? api.GetErrorString(r__) : "NCCL error"); \
+  } while (0)
+int pf_comm_unique_id(void* id128) {
+  if (!id128) return fail(PF_ERR_ARG, "pf_comm_unique_id: null argument");
+  const NcclApi& api = nccl_api();
+  if (api.error) return fail(PF_ERR_CUDA, "%s", api.error);
+  static_assert(sizeof(NcclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  NCCL_TRY(api.GetUniqueId((NcclUniqueId*)id128));
+  return PF_OK;
+}
+int pf_comm_create(int device, int rank, int nranks, const void* id128, pf_comm_handle* out) {
+  if (!id128 || !out || nranks < 1 || rank < 0 || rank >= nranks) return fail(PF_ERR_ARG, "pf_comm_create: bad argument");
+  const NcclApi& api = nccl_api();
+  if (api.error) return fail(PF_ERR_CUDA, "%s", api.error);
+  CU(cudaSetDevice(device));
+  NcclUniqueId id;
+  memcpy(&id, id128, sizeof id);
+  pf_comm* c = new pf_comm();
+  c->device = device; c->rank = rank; c->nranks = nranks;
+  const int r = api.CommInitRank(&c->comm, nranks, id, rank);
+  if (r != kNcclSuccess) { delete c; return fail(PF_ERR_CUDA, "ncclCommInitRank: %s", api.GetErrorString(r)); }
+  *out = c;
+  return PF_OK;
+}
+int pf_comm_destroy(pf_comm_handle c) {
+  if (!c) return PF_OK;
+  const NcclApi& api = nccl_api();
+  cudaSetDevice(c->device);
+  if (c->comm && api.CommDestroy) api.CommDestroy(c->comm);
+  delete c;
+  return PF_OK;
+}
+int pf_gather(pf_comm_handle c, int root, int count, void* const* dev_ptrs, const int64_t* bytes, const int32_t* peer, void* stream) {
+  if (!c || count < 0 || root < 0 || root >= c->nranks || (count > 0 && (!dev_ptrs || !bytes))) return fail(PF_ERR_ARG, "pf_gather: bad argument");
+  if (c->rank == root && count > 0 && !peer) return fail(PF_ERR_ARG, "pf_gather: the root needs the source rank of every segment");
+  const NcclApi& api = nccl_api();
+  CU(cudaSetDevice(c->device));
+  if (count == 0) return PF_OK;
+  NCCL_TRY(api.GroupStart());
+  for (int i = 0; i < count; ++i) {
+    int r;
+    if (c->rank == root) {
+      if (peer[i] < 0 || peer[i] >= c->nranks || peer[i] == root) { api.GroupEnd(); return fail(PF_ERR_ARG, "pf_gather: segment %d comes from rank %d", i, peer[i]); }
+      r = api.Recv(dev_ptrs[i], (size_t)bytes[i], kNcclUint8, peer[i], c->comm, (cudaStream_t)stream);
+    } else {
+      r = api.Send(dev_ptrs[i], (size_t)bytes[i], kNcclUint8, root, c->comm, (cudaStream_t)stream);
+    }
+    if (r != kNcclSuccess) { api.GroupEnd(); return fail(PF_ERR_CUDA, "ncclSend/Recv: %s", api.GetErrorString(r)); }
+  }
+  NCCL_TRY(api.GroupEnd());
+  return PF_OK;
+}
+
+// ---- decode front-end (nvJPEG) ------------------------------------------------------------------
+int pf_jpeg_create(int device, int max_threads, pf_jpeg_handle* out) {
+  if (!out) return fail(PF_ERR_ARG, "pf_jpeg_create: null argument");
+  const NvjpegApi& api = nvjpeg_api();
+  if (api.error) return fail(PF_ERR_CUDA, "%s", api.error);
+  CU(cudaSetDevice(device));
+  pf_jpeg* j = new pf_jpeg();
+  j->device = device;
+  if (api.CreateSimple(&j->handle) != NVJPEG_STATUS_SUCCESS) { delete j; return fail(PF_ERR_CUDA, "nvjpegCreateSimple failed"); }
+  int nt = max_threads > 0 ? max_threads : (int)std::thread::hardware_concurrency() / 2;
+  nt = nt < 1 ? 1 : (nt > 32 ? 32 : nt);
+  j->workers.resize(nt);
+  bool ok = cudaEventCreateWithFlags(&j->start, cudaEventDisableTiming) == cudaSuccess;
+  for (auto& w : j->workers) {
+    ok = ok && api.StateCreate(j->handle, &w.state) == NVJPEG_STATUS_SUCCESS;
+    ok = ok && cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming) == cudaSuccess;
+  }
+  if (!ok) { pf_jpeg_destroy(j); return fail(PF_ERR_CUDA, "pf_jpeg_create: decoder state / stream creation failed"); }
+  *out = j;
+  return PF_OK;
+}
+int pf_jpeg_destroy(pf_jpeg_handle j) {
+  if (!j) return PF_OK;
+  const NvjpegApi& api = nvjpeg_api();
+  cudaSetDevice(j->device);
+  for (auto& w : j->workers) {
+    if (w.stream) cudaStreamSynchronize(w.stream);
+    if (w.state) api.StateDestroy(w.state);
+    if (w.stream) cudaStreamDestroy(w.stream);
+    if (w.done) cudaEventDestroy(w.done);
+  }
+  if (j->start) cudaEventDestroy(j->start);
+  if (j->handle) api.Destroy(j->handle);
+  delete j;
+  return PF_OK;
+}
+int pf_jpeg_info(pf_jpeg_handle j, const uint8_t* data, int64_t length, int32_t* height, int32_t* width) {
+  if (!j || !data || length < 4 || !height || !width) return fail(PF_ERR_ARG, "pf_jpeg_info: bad argument");
+  const NvjpegApi& api = nvjpeg_api();
+  int nc = 0, ws[NVJPEG_MAX_COMPONENT] = {0}, hs[NVJPEG_MAX_COMPONENT] = {0};
+  nvjpegChromaSubsampling_t ss;
+  if (api.GetImageInfo(j->handle, data, (size_t)length, &nc, &ss, ws, hs) != NVJPEG_STATUS_SUCCESS) return fail(PF_ERR_ARG, "pf_jpeg_info: not a decodable JPEG stream");
+  *height = hs[0]; *width = ws[0];
+  return PF_OK;
+}
+int pf_jpeg_decode_batch(pf_jpeg_handle j, int n, const uint8_t* const* data, const int64_t* length, const int32_t* height, const int32_t* width,
+                         uint8_t* blob, const int64_t* offset, void* stream) {
+  if (!j || n < 1 || !data || !length || !height || !width || !blob || !offset) return fail(PF_ERR_ARG, "pf_jpeg_decode_batch: bad argument");
+  const NvjpegApi& api = nvjpeg_api();
+  CU(cudaSetDevice(j->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  // the workers' streams start after everything already queued on the caller's stream (the blob may be in use by an earlier forward)
+  CU(cudaEventRecord(j->start, st));
+  const int nt = (int)j->workers.size() < n ? (int)j->workers.size() : n;
+  std::atomic<int> next{0}, failed{-1};
+  auto work = [&](int t) {
+    cudaSetDevice(j->device);
+    pf_jpeg::Worker& w = j->workers[t];
+    cudaStreamWaitEvent(w.stream, j->start, 0);
+    for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) {
+      nvjpegImage_t dst{};
+      dst.channel[0] = blob + offset[i];
+      dst.pitch[0] = (size_t)width[i] * 3;
+      if (api.Decode(j->handle, w.state, data[i], (size_t)length[i], NVJPEG_OUTPUT_BGRI, &dst, w.stream) != NVJPEG_STATUS_SUCCESS) failed.store(i);
+    }
+    cudaEventRecord(w.done, w.stream);
+  };
+  std::vector<std::thread> threads;
+  for (int t = 1; t < nt; ++t) threads.emplace_back(work, t);
+  work(0);
+  for (auto& th : threads) th.join();
+  for (int t = 0; t < nt; ++t) CU(cudaStreamWaitEvent(st, j->workers[t].done, 0));
+  if (failed.load() >= 0) return fail(PF_ERR_ARG, "pf_jpeg_decode_batch: image %d could not be decoded", failed.load());
+  return PF_OK;
+}
+
 // ---- single-operator entry points ------------------------------------------------------------------------
 int pf_op_conv_gemm(const float* x, int B, int H, int W, int Cin, const void* whi, const void* wlo, const float* bias, int N, int KH, int KW,
-                    int stride, int pad, int in_relu, int act, const float* res, int res_relu, float* y, int engine, void* stream) {
-  ConvGemmParams p{};
-  p.A = x; p.lda = Cin; p.B = B; p.H = H; p.W = W; p.Cin = Cin;
-  p.KH = KH; p.KW = KW; p.stride = stride; p.pad = pad;
-  p.OH = (H + 2 * pad - KH) / stride + 1; p.OW = (W + 2 * pad - KW) / stride + 1;
-  p.in_relu = in_relu;
-  p.Whi = (const __nv_bfloat16*)whi; p.Wlo = (const __nv_bfloat16*)wlo; p.N = N; p.K = KH * KW * Cin;
-  p.bias = bias; p.bias_mode = bias ? 1 : 0; p.act = act;
-  p.res = res; p.ldr = N; p.res_relu = res_relu;
-  p.C = y; p.ldc = N; p.groups = 1;
-  if (engine == 3) {
-    // TMA engine: split the input the way a producer kernel would, then run the same helpers the forward graph uses
-    if (KH != KW) return fail(PF_ERR_ARG, "pf_op_conv_gemm: square filters only");
-    cudaStream_t st = (cudaStream_t)stream;
-    int dev = 0;
-    CU(cudaGetDevice(&dev));
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, dev));
-    static pf_engine tmp;
-    tmp.sm_count = prop.multiProcessorCount;
-    tmp.profile = false; tmp.debug = false;
-    const long long nx = (long long)B * H * W * Cin;
-    const long long colb = (long long)B * p.OH * p.OW * KH * KW * Cin * 4 + (1 << 20);
-    char* scratch = nullptr;
-    CU(cudaMalloc(&scratch, nx * 4 + colb + 4096));
-    Fwd F{&tmp, Arena{}, st, false, B};
-    F.ar.base = scratch; F.ar.cap = nx * 4 + colb + 4096;
-    SplitT A = F.salloc((long long)B * H * W, Cin);
-    LAUNCHED((split_kernel<<<(unsigned)cdivl(nx, 256), 256, 0, st>>>(x, A.hi, A.lo, nx, in_relu), cudaGetLastError()));
-    GemmW w{(const __nv_bfloat16*)whi, (const __nv_bfloat16*)wlo, bias};
-    Fwd::Epi o;
-    o.C = y; o.ldc = N; o.act = act; o.res = res; o.ldr = N; o.res_relu = res_relu;
-    int r;
+                    int stride, int pad, int in_relu, int act, const float* res, int res_relu, float* y, void* stream) {
+  // split the input the way a producer kernel would, then run the same helpers the forward graph uses
+  if (!x || !whi || !wlo || !y) return fail(PF_ERR_ARG, "pf_op_conv_gemm: null argument");
+  if (KH != KW) return fail(PF_ERR_ARG, "pf_op_conv_gemm: square filters only");
+  TRY(configure_current_device());
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, dev));
+  pf_engine tmp;
+  tmp.device = dev;
+  tmp.sm_count = prop.multiProcessorCount;
+  const int OH = (H + 2 * pad - KH) / stride + 1, OW = (W + 2 * pad - KW) / stride + 1;
+  const long long nx = (long long)B * H * W * Cin;
+  const long long colb = (long long)B * OH * OW * KH * KW * Cin * 4 + (1 << 20);
+  char* scratch = nullptr;
+  CU(cudaMalloc(&scratch, nx * 4 + colb + 4096));
+  Fwd F{&tmp, Arena{}, st, false, B};
+  F.ar.base = scratch; F.ar.cap = nx * 4 + colb + 4096;
+  SplitT A = F.salloc((long long)B * H * W, Cin);
+  int r = PF_OK;
+  {
+    cudaError_t le = (split_kernel<<<(unsigned)cdivl(nx, 256), 256, 0, st>>>(x, A.hi, A.lo, nx, in_relu), cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (le != cudaSuccess) r = fail(PF_ERR_CUDA, "split_kernel: %s", cudaGetErrorString(le));
+  }
+  GemmW w{(const __nv_bfloat16*)whi, (const __nv_bfloat16*)wlo, bias};
+  Fwd::Epi o;
+  o.C = y; o.ldc = N; o.act = act; o.res = res; o.ldr = N; o.res_relu = res_relu;
+  if (r == PF_OK) {
     if (KH == 3 && stride == 1 && pad == 1 && Cin % 64 == 0) r = F.thalo(A, 0, 0, nullptr, 0, 0, B, H, W, Cin, w, N, 1, 0, o);
     else if (KH == 1 && stride == 1 && pad == 0) r = F.tgemm(A, (long long)B * H * W, Cin, 0, w, N, o);
     else r = F.tconv_gather(A, B, H, W, Cin, KH, stride, pad, w, N, o);
-    cudaError_t se = cudaStreamSynchronize(st);
-    cudaFree(scratch);
-    if (r != PF_OK) return r;
-    if (se != cudaSuccess) return fail(PF_ERR_CUDA, "TMA engine: %s", cudaGetErrorString(se));
-    return PF_OK;
   }
-  if (engine == 2) {
-    if (!conv3x3_tc_eligible(p)) return fail(PF_ERR_ARG, "pf_op_conv_gemm: shape not eligible for the halo-tile 3x3 kernel");
-    LAUNCHED(conv3x3_tc_launch(p, (cudaStream_t)stream));
-    return PF_OK;
-  }
-  if (engine == 1) {
-    const char* msg = conv_gemm_tc_check(p);
-    if (msg) return fail(PF_ERR_ARG, "%s", msg);
-    LAUNCHED(conv_gemm_tc_launch(p, (cudaStream_t)stream));
-    return PF_OK;
-  }
-  const char* msg = conv_gemm_check(p);
-  if (msg) return fail(PF_ERR_ARG, "%s", msg);
-  LAUNCHED(conv_gemm_launch(p, (cudaStream_t)stream));
+  cudaError_t se = cudaStreamSynchronize(st);
+  cudaFree(scratch);
+  if (r != PF_OK) return r;
+  if (se != cudaSuccess) return fail(PF_ERR_CUDA, "pf_op_conv_gemm: %s", cudaGetErrorString(se));
   return PF_OK;
 }
 int pf_camera_fields(int device, const pf_camera* cams, int n, float* up, float* lat, void* stream) {
@@ -1340,7 +1326,7 @@ int pf_camera_fields(int device, const pf_camera* cams, int n, float* up, float*
   for (int i0 = 0; i0 < n; i0 += kCamChunk) {
     const int m = n - i0 < kCamChunk ? n - i0 : kCamChunk;
     CamBatch b{};
-    long long max_px = 1;
+    long long max_q = 1;
     for (int i = 0; i < m; ++i) {
       const pf_camera& c = cams[i0 + i];
       if (c.height < 1 || c.width < 1 || !(c.focal_rel != 0.0)) return fail(PF_ERR_ARG, "pf_camera_fields: image %d: size %dx%d, focal %g", i0 + i, c.height, c.width, c.focal_rel);
@@ -1352,13 +1338,76 @@ int pf_camera_fields(int device, const pf_camera* cams, int n, float* up, float*
       o.sr = sin(c.roll); o.cr = cos(c.roll); o.se = sin(c.elevation); o.ce = cos(c.elevation);
       o.sgn = c.elevation > 0 ? 1.0 : (c.elevation < 0 ? -1.0 : 0.0);
       o.up_off = c.up_offset; o.lat_off = c.lat_offset;
-      const long long px = (long long)c.height * c.width;
-      if (px > max_px) max_px = px;
+      const long long qd = (long long)c.height * ((c.width + 3) / 4);
+      if (qd > max_q) max_q = qd;
     }
-    const dim3 grid((unsigned)cdivl(max_px, 256), (unsigned)m);
+    const dim3 grid((unsigned)cdivl(max_q, 256), (unsigned)m);
     LAUNCHED((camera_fields_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(b, up, lat), cudaGetLastError()));
   }
   return PF_OK;
+}
+
+static int upload_table(const ResampleTable& t, int** bounds, int** coeffs) {
+  CU(cudaMalloc(bounds, t.bounds.size() * 4));
+  CU(cudaMalloc(coeffs, t.coeffs.size() * 4));
+  CU(cudaMemcpy(*bounds, t.bounds.data(), t.bounds.size() * 4, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(*coeffs, t.coeffs.data(), t.coeffs.size() * 4, cudaMemcpyHostToDevice));
+  return PF_OK;
+}
+int pf_op_resize_u8(const uint8_t* img, int H, int W, int new_h, int new_w, uint8_t* out, void* stream) {
+  if (!img || !out || H < 1 || W < 1 || new_h < 1 || new_w < 1) return fail(PF_ERR_ARG, "pf_op_resize_u8: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (H == new_h && W == new_w) {   // Pillow returns a copy when the size does not change
+    CU(cudaMemcpyAsync(out, img, (size_t)H * W * 3, cudaMemcpyDeviceToDevice, st));
+    return PF_OK;
+  }
+  ResampleTable tx = make_resample_table(W, new_w), ty = make_resample_table(H, new_h);
+  int *bx = nullptr, *cx = nullptr, *by = nullptr, *cy = nullptr;
+  unsigned char* tmp = nullptr;
+  int r = upload_table(tx, &bx, &cx);
+  if (r == PF_OK) r = upload_table(ty, &by, &cy);
+  if (r == PF_OK && cudaMalloc(&tmp, (size_t)H * new_w * 3) != cudaSuccess) r = fail(PF_ERR_CUDA, "pf_op_resize_u8: cudaMalloc");
+  if (r == PF_OK) {
+    // Pillow runs the horizontal pass first (over the rows the vertical pass needs: all of them here), each pass rounded to uint8
+    cudaError_t le = (resize_u8_h_kernel<<<(unsigned)cdivl((long long)H * new_w, 256), 256, 0, st>>>(img, H, W, new_w, bx, cx, tx.ksize, tmp), cudaGetLastError());
+    if (le == cudaSuccess) le = (resize_u8_v_kernel<<<(unsigned)cdivl((long long)new_h * new_w, 256), 256, 0, st>>>(tmp, H, new_w, new_h, by, cy, ty.ksize, out), cudaGetLastError());
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+    if (le == cudaSuccess) le = cudaStreamSynchronize(st);
+    if (le != cudaSuccess) r = fail(PF_ERR_CUDA, "pf_op_resize_u8: %s", cudaGetErrorString(le));
+  }
+  cudaFree(bx); cudaFree(cx); cudaFree(by); cudaFree(cy); cudaFree(tmp);
+  return r;
+}
+int pf_op_resize_f32(const float* img, int H, int W, int C, int new_h, int new_w, float* out, void* stream) {
+  if (!img || !out || H < 1 || W < 1 || C < 1 || new_h < 1 || new_w < 1) return fail(PF_ERR_ARG, "pf_op_resize_f32: bad argument");
+  LAUNCHED((resize_f32_kernel<<<(unsigned)cdivl((long long)new_h * new_w * C, 256), 256, 0, (cudaStream_t)stream>>>(img, H, W, C, new_h, new_w, out), cudaGetLastError()));
+  return PF_OK;
+}
+int pf_op_argmax_decode(const float* logits, float* field, int B, int HW, int NC, int is_gravity, void* stream) {
+  if (!logits || !field || B < 1 || HW < 1 || NC < 1) return fail(PF_ERR_ARG, "pf_op_argmax_decode: bad argument");
+  LAUNCHED((argmax_decode_kernel<<<(unsigned)cdivl((long long)B * HW, 256), 256, 0, (cudaStream_t)stream>>>(logits, field, B, HW, NC, is_gravity), cudaGetLastError()));
+  return PF_OK;
+}
+int pf_op_pred_argmax_decode(const float* feat, int ld, int coff, const float* w, const float* bias, float* field, int B, int HW, int NC, int is_gravity,
+                             void* stream) {
+  if (!feat || !w || !bias || !field || B < 1 || HW < 1 || NC < 1 || NC > 256 || (ld & 3) || (coff & 3)) return fail(PF_ERR_ARG, "pf_op_pred_argmax_decode: bad argument");
+  LAUNCHED((pred_argmax_decode_kernel<<<ew_grid((long long)B * HW * 4), 256, NC * 37 * 4, (cudaStream_t)stream>>>(feat, ld, coff, w, bias, field, B, HW, NC, is_gravity),
+            cudaGetLastError()));
+  return PF_OK;
+}
+int pf_op_postprocess(const float* vec, const float* lat, int n, const int32_t* height, const int32_t* width, float* gravity_original,
+                      const int64_t* gravity_original_offset, float* latitude_original, const int64_t* latitude_original_offset, int lat_is_sin,
+                      void* stream) {
+  if (!vec || !lat || n < 1 || !height || !width || !gravity_original || !gravity_original_offset || !latitude_original || !latitude_original_offset)
+    return fail(PF_ERR_ARG, "pf_op_postprocess: bad argument");
+  PostImage* d_post = nullptr;
+  CU(cudaMalloc(&d_post, n * sizeof(PostImage)));
+  int r = launch_postprocess(vec, lat, n, height, width, gravity_original_offset, latitude_original_offset, gravity_original, latitude_original,
+                             lat_is_sin, d_post, (cudaStream_t)stream);
+  cudaError_t se = cudaStreamSynchronize((cudaStream_t)stream);
+  cudaFree(d_post);
+  if (r == PF_OK && se != cudaSuccess) r = fail(PF_ERR_CUDA, "pf_op_postprocess: %s", cudaGetErrorString(se));
+  return r;
 }
 
 int pf_op_layernorm(const float* x, float* y, int64_t rows, int C, const float* w, const float* b, float eps, void* stream) {
@@ -1366,11 +1415,13 @@ int pf_op_layernorm(const float* x, float* y, int64_t rows, int C, const float* 
   return PF_OK;
 }
 int pf_op_attention(const float* q, const float* kv, float* out, int B, int N, int C, int heads, void* stream) {
+  TRY(configure_current_device());
   if (C != heads * kAttnD) return fail(PF_ERR_ARG, "pf_op_attention: head_dim must be 64");
   LAUNCHED(attention_launch(q, kv, out, B, N, C, heads, (cudaStream_t)stream));
   return PF_OK;
 }
 int pf_op_attention_mma(const float* q, const float* kv, float* out, int B, int N, int C, int heads, void* stream) {
+  TRY(configure_current_device());
   if (C != heads * kAmD) return fail(PF_ERR_ARG, "pf_op_attention_mma: head_dim must be 64");
   LAUNCHED(attention_mma_launch(q, kv, out, B, N, C, heads, (cudaStream_t)stream));
   return PF_OK;
@@ -1391,6 +1442,7 @@ int pf_op_upsample2x(const float* x, float* y, int B, int H, int W, int C, void*
   return PF_OK;
 }
 int pf_op_preprocess(const uint8_t* img, int H, int W, const float* mean3, const float* std3, float* y, void* stream) {
+  TRY(configure_current_device());
   // standalone tables (not cached): test entry point only
   ResampleTable tx = make_resample_table(W, kNet), ty = make_resample_table(H, kNet);
   if (ty.ksize + 1 > kPreMaxSmemRows) return fail(PF_ERR_ARG, "image too tall");
@@ -1408,7 +1460,6 @@ int pf_op_preprocess(const uint8_t* img, int H, int W, const float* mean3, const
   int rows = pre_rows_needed(H);
   if (rows > kPreMaxSmemRows) rows = kPreMaxSmemRows;
   const int smem = rows * kNet * 3;
-  CU(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem > 48 * 1024 ? smem : 48 * 1024));
   LAUNCHED((preprocess_kernel<<<dim3(kNet / kPreRows, 1), kNet, smem, (cudaStream_t)stream>>>(img, d, y, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2], rows),
             cudaGetLastError()));
   CU(cudaStreamSynchronize((cudaStream_t)stream));

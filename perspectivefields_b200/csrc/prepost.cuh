@@ -153,55 +153,120 @@ struct PostImage {
   long long pix0;   // first global output-pixel index of this image (prefix sum of H*W)
 };
 
-// grid = (blocks over the largest image, n images); one thread = 4 consecutive output pixels of one row (16 B stores to each
-// of the three planes).  Reads hit L1/L2 (the 320x320 source of an image is 1.2 MB); the kernel is bound by its writes.
-__global__ void __launch_bounds__(256) postprocess_kernel(const float* __restrict__ vec, const float* __restrict__ lat, const PostImage* __restrict__ imgs, int n,
-                                                          long long total, float* __restrict__ g_out, float* __restrict__ l_out, int lat_is_sin) {
-  const int img = blockIdx.y;
-  const PostImage im = imgs[img];
-  const int W4 = (im.W + 3) >> 2;
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= im.H * W4) return;
-  const int y = q / W4, x0 = (q - y * W4) * 4;
+// asin for |x| <= 1, branch-free (Cephes-style): |x| <= 1/2: x + x z P(z), z = x^2; else pi/2 - 2 (s + s z P(z)), z = (1 - |x|)/2,
+// s = sqrt z.  Max error 1.7e-7 rad against float64 asin over 4e6 samples incl. the end points (tests/test_host_logic.py repeats
+// the check on these coefficients); libm's asinf costs ~3x the instructions and made this kernel instruction-bound.
+__device__ __forceinline__ float fast_asinf(float x) {
+  const float a = fabsf(x);
+  const bool big = a > 0.5f;
+  const float z = big ? (1.0f - a) * 0.5f : a * a;
+  const float s = big ? sqrtf(z) : a;
+  float p = 4.2163199048e-2f;
+  p = fmaf(p, z, 2.4181311049e-2f);
+  p = fmaf(p, z, 4.5470025998e-2f);
+  p = fmaf(p, z, 7.4953002686e-2f);
+  p = fmaf(p, z, 1.6666752422e-1f);
+  float r = fmaf(s * z, p, s);
+  r = big ? 1.5707963267948966f - (r + r) : r;
+  return copysignf(r, x);
+}
+
+// Block = (band of kPostBand output rows, image).  Per group of kPostRows output rows the block first interpolates VERTICALLY:
+// for each of the 320 source columns and the three source planes (gravity x * W/320, gravity y * H/320, latitude) it stores
+// hy * src[y0][x] + ly * src[y1][x] in shared memory; then every thread produces 4 consecutive output pixels of one row from
+// two shared-memory taps per plane (per-column index / weight tables, built once per block), normalises the up-vector, applies
+// asin + rad2deg and writes three 16-byte streaming stores.  12 global loads per pixel become 6 shared loads, and the per-pixel
+// index arithmetic disappears: the kernel is bound by its 12 B/pixel of stores (bench.py roofline_post).
+// The interpolation is evaluated as hx * (hy v00 + ly v10) + lx * (hy v01 + ly v11): ATen's bilinear kernel nests the two axes the
+// other way round (same weights, same products; the results differ by fp32 rounding only, ~1e-7 relative).
+constexpr int kPostRows = 4, kPostBand = 16, kPostThreads = 256, kPostMaxW = 4096;
+__global__ void __launch_bounds__(kPostThreads) postprocess_kernel(const float* __restrict__ vec, const float* __restrict__ lat, const PostImage* __restrict__ imgs,
+                                                                   float* __restrict__ g_out, float* __restrict__ l_out, int lat_is_sin) {
+  __shared__ float s_v[kPostRows][3][kNet + 1];      // vertically interpolated source rows (+1: tap xa + 1 of the last column)
+  extern __shared__ __align__(16) unsigned char s_dyn[];   // per output column: int xa, float lx  (W entries each, W padded to 4)
+  const PostImage im = imgs[blockIdx.y];
+  const int band0 = blockIdx.x * kPostBand;
+  if (band0 >= im.H) return;
+  const int W4 = (im.W + 3) >> 2, Wp = W4 * 4;
+  int* s_xa = reinterpret_cast<int*>(s_dyn);
+  float* s_lx = reinterpret_cast<float*>(s_dyn) + Wp;
+  const int tid = threadIdx.x;
   const float sch = (float)kNet / (float)im.H, scw = (float)kNet / (float)im.W;
-  const float sy = fmaxf(sch * ((float)y + 0.5f) - 0.5f, 0.f);
-  const int y0 = min((int)sy, kNet - 1);
-  const int y1 = y0 + (y0 < kNet - 1);
-  const float ly = sy - (float)y0, hy = 1.f - ly;
-  const float* v0 = vec + (long long)img * 2 * kNet * kNet;
+  const bool tab = Wp <= kPostMaxW;       // wider images: indices / weights are recomputed per pixel instead
+  for (int x = tid; tab && x < Wp; x += kPostThreads) {
+    const int xc = min(x, im.W - 1);
+    const float sx = fmaxf(scw * ((float)xc + 0.5f) - 0.5f, 0.f);
+    const int xa = min((int)sx, kNet - 1);
+    s_xa[x] = xa;
+    s_lx[x] = sx - (float)xa;
+  }
+  const float* v0 = vec + (long long)blockIdx.y * 2 * kNet * kNet;
   const float* v1 = v0 + kNet * kNet;
-  const float* lp = lat + (long long)img * kNet * kNet;
+  const float* lp = lat + (long long)blockIdx.y * kNet * kNet;
   // the reference scales the field before resampling: vec * [[W/320],[H/320]] (float32 tensor built from python doubles)
   const float fx = (float)((double)im.W / (double)kNet), fy = (float)((double)im.H / (double)kNet);
-  float ogx[4], ogy[4], ol[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int x = min(x0 + j, im.W - 1);
-    const float sx = fmaxf(scw * ((float)x + 0.5f) - 0.5f, 0.f);
-    const int xa = min((int)sx, kNet - 1);
-    const int xb = xa + (xa < kNet - 1);
-    const float lx = sx - (float)xa, hx = 1.f - lx;
-    const int i00 = y0 * kNet + xa, i01 = y0 * kNet + xb, i10 = y1 * kNet + xa, i11 = y1 * kNet + xb;
-    const float gx = hy * (hx * (v0[i00] * fx) + lx * (v0[i01] * fx)) + ly * (hx * (v0[i10] * fx) + lx * (v0[i11] * fx));
-    const float gy = hy * (hx * (v1[i00] * fy) + lx * (v1[i01] * fy)) + ly * (hx * (v1[i10] * fy) + lx * (v1[i11] * fy));
-    const float nrm = fmaxf(sqrtf(gx * gx + gy * gy), 1e-12f);
-    ogx[j] = gx / nrm; ogy[j] = gy / nrm;
-    float lv = hy * (hx * lp[i00] + lx * lp[i01]) + ly * (hx * lp[i10] + lx * lp[i11]);
-    if (lat_is_sin) lv = asinf(lv) * (180.0f / 3.14159265358979323846f);
-    ol[j] = lv;
-  }
   const long long HW = (long long)im.H * im.W;
-  const long long p = (long long)y * im.W + x0;
-  float* gp = g_out + im.g_off + p;
-  float* lpo = l_out + im.l_off + p;
-  if (x0 + 3 < im.W && ((im.g_off + p) & 3) == 0 && ((im.g_off + HW + p) & 3) == 0 && ((im.l_off + p) & 3) == 0) {
-    *reinterpret_cast<float4*>(gp) = make_float4(ogx[0], ogx[1], ogx[2], ogx[3]);
-    *reinterpret_cast<float4*>(gp + HW) = make_float4(ogy[0], ogy[1], ogy[2], ogy[3]);
-    *reinterpret_cast<float4*>(lpo) = make_float4(ol[0], ol[1], ol[2], ol[3]);
-  } else {
-    for (int j = 0; j < 4 && x0 + j < im.W; ++j) { gp[j] = ogx[j]; gp[HW + j] = ogy[j]; lpo[j] = ol[j]; }
+  const bool vec_ok = (im.W & 3) == 0 && (im.g_off & 3) == 0 && ((im.g_off + HW) & 3) == 0 && (im.l_off & 3) == 0;
+  const int band1 = min(band0 + kPostBand, im.H);
+  for (int r0 = band0; r0 < band1; r0 += kPostRows) {
+    __syncthreads();     // (the previous group's readers are done; the column tables are complete)
+    for (int i = tid; i < kPostRows * kNet; i += kPostThreads) {
+      const int rr = i / kNet, x = i - rr * kNet;
+      const int y = min(r0 + rr, im.H - 1);
+      const float sy = fmaxf(sch * ((float)y + 0.5f) - 0.5f, 0.f);
+      const int y0 = min((int)sy, kNet - 1);
+      const int y1 = y0 + (y0 < kNet - 1);
+      const float ly = sy - (float)y0, hy = 1.f - ly;
+      const int i0 = y0 * kNet + x, i1 = y1 * kNet + x;
+      s_v[rr][0][x] = hy * (__ldg(v0 + i0) * fx) + ly * (__ldg(v0 + i1) * fx);
+      s_v[rr][1][x] = hy * (__ldg(v1 + i0) * fy) + ly * (__ldg(v1 + i1) * fy);
+      s_v[rr][2][x] = hy * __ldg(lp + i0) + ly * __ldg(lp + i1);
+      if (x == kNet - 1) { s_v[rr][0][kNet] = s_v[rr][0][x]; s_v[rr][1][kNet] = s_v[rr][1][x]; s_v[rr][2][kNet] = s_v[rr][2][x]; }
+    }
+    __syncthreads();
+    const int rows = min(kPostRows, band1 - r0);
+    for (int it = tid; it < rows * W4; it += kPostThreads) {
+      const int rr = it / W4, x0 = (it - rr * W4) * 4;
+      int xa[4];
+      float lx[4];
+      if (tab) {
+        const int4 xa4 = *reinterpret_cast<const int4*>(s_xa + x0);
+        const float4 lx4 = *reinterpret_cast<const float4*>(s_lx + x0);
+        xa[0] = xa4.x; xa[1] = xa4.y; xa[2] = xa4.z; xa[3] = xa4.w;
+        lx[0] = lx4.x; lx[1] = lx4.y; lx[2] = lx4.z; lx[3] = lx4.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float sx = fmaxf(scw * ((float)min(x0 + j, im.W - 1) + 0.5f) - 0.5f, 0.f);
+          xa[j] = min((int)sx, kNet - 1);
+          lx[j] = sx - (float)xa[j];
+        }
+      }
+      float ogx[4], ogy[4], ol[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        // tap xa + 1 is clamped to column 319 through the duplicated entry s_v[..][320] (its weight lx is 0 there anyway)
+        const float hx = 1.f - lx[j];
+        const float gx = hx * s_v[rr][0][xa[j]] + lx[j] * s_v[rr][0][xa[j] + 1];
+        const float gy = hx * s_v[rr][1][xa[j]] + lx[j] * s_v[rr][1][xa[j] + 1];
+        float lv = hx * s_v[rr][2][xa[j]] + lx[j] * s_v[rr][2][xa[j] + 1];
+        const float inv = 1.0f / fmaxf(sqrtf(gx * gx + gy * gy), 1e-12f);     // F.normalize: v / max(|v|, eps)
+        ogx[j] = gx * inv; ogy[j] = gy * inv;
+        if (lat_is_sin) lv = fast_asinf(lv) * (180.0f / 3.14159265358979323846f);
+        ol[j] = lv;
+      }
+      const long long p = (long long)(r0 + rr) * im.W + x0;
+      float* gp = g_out + im.g_off + p;
+      float* lpo = l_out + im.l_off + p;
+      if (vec_ok) {
+        __stcs(reinterpret_cast<float4*>(gp), make_float4(ogx[0], ogx[1], ogx[2], ogx[3]));
+        __stcs(reinterpret_cast<float4*>(gp + HW), make_float4(ogy[0], ogy[1], ogy[2], ogy[3]));
+        __stcs(reinterpret_cast<float4*>(lpo), make_float4(ol[0], ol[1], ol[2], ol[3]));
+      } else {
+        for (int j = 0; j < 4 && x0 + j < im.W; ++j) { gp[j] = ogx[j]; gp[HW + j] = ogy[j]; lpo[j] = ol[j]; }
+      }
+    }
   }
-  (void)n; (void)total;
 }
 
 // =====================================================================================================
@@ -222,34 +287,140 @@ struct CamImage {
 constexpr int kCamChunk = 24;   // images per launch (the descriptors travel as a kernel parameter)
 struct CamBatch { CamImage im[kCamChunk]; };
 
+// atan2(y, h) in DEGREES for h >= 0 (Cephes-style atanf: three ranges, odd polynomial on |r| <= tan(pi/8)); the range offset is
+// added in float64 so that the result is rounded to float32 once.  Max error 7.2e-6 degrees incl. that final rounding
+// (ulp(90)/2 = 3.8e-6), checked against float64 atan2 in tests/test_host_logic.py.
+__device__ __forceinline__ float fast_atan2_deg(float y, float h) {
+  const float a = fabsf(y);
+  const bool hi = a > 2.414213562373095f * h, mid = !hi && a > 0.4142135623730950f * h;
+  const float num = hi ? -h : (mid ? a - h : a), den = hi ? a : (mid ? a + h : h);
+  const float r = num / den;
+  const float z = r * r;
+  float p = 8.05374449538e-2f;
+  p = fmaf(p, z, -1.38776856032e-1f);
+  p = fmaf(p, z, 1.99777106478e-1f);
+  p = fmaf(p, z, -3.33329491539e-1f);
+  const float pr = fmaf(r * z, p, r);
+  const double off = hi ? 90.0 : (mid ? 45.0 : 0.0);
+  const float deg = (float)fma((double)pr, 57.29577951308232, off);
+  return copysignf(deg, y);
+}
+
+// One thread = 4 consecutive pixels of one row.  The pixel -> ray map is linear: its three world components are evaluated in
+// float64 (x_j = linspace sample, one DFMA per component: 1e-16 relative, like the numpy reference), then rounded to float32 for
+// the square root, the division and the arctangent (fast_atan2_deg) -- the float64 sqrt / divide / atan2 per pixel of the first
+// version kept this kernel at 0.11 of the HBM roofline; it is now bound by its 12 B/pixel of stores.
 __global__ void __launch_bounds__(256) camera_fields_kernel(const __grid_constant__ CamBatch batch, float* __restrict__ up, float* __restrict__ lat) {
   const CamImage& c = batch.im[blockIdx.y];
-  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= (long long)c.H * c.W) return;
-  const int i = (int)(p / c.W), j = (int)(p - (long long)i * c.W);
+  const int W4 = (c.W + 3) >> 2;
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (long long)c.H * W4) return;
+  const int i = (int)(q / W4), j0 = (int)(q - (long long)i * W4) * 4;
+  const long long p0 = (long long)i * c.W + j0;
+  const int nj = min(4, c.W - j0);
   if (up) {
-    double vx, vy;
-    if (c.sgn == 0.0) { vx = -c.sr; vy = -c.cr; }
-    else {
+    float o[8];
+    if (c.sgn == 0.0) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { o[2 * k] = (float)(-c.sr); o[2 * k + 1] = (float)(-c.cr); }
+    } else {
       const double vvp_x = (c.sr * c.ce * c.f) / -c.se + c.cx, vvp_y = (c.cr * c.ce * c.f) / -c.se + c.cy;
-      vx = (vvp_x - ((double)j + 0.5)) * c.sgn;
-      vy = (vvp_y - ((double)i + 0.5)) * c.sgn;
+      const float vy = (float)((vvp_y - ((double)i + 0.5)) * c.sgn);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float vx = (float)((vvp_x - ((double)(j0 + k) + 0.5)) * c.sgn);
+        const float inv = rsqrtf(fmaf(vx, vx, vy * vy));
+        o[2 * k] = vx * inv; o[2 * k + 1] = vy * inv;
+      }
     }
-    const double n = sqrt(vx * vx + vy * vy);
-    *reinterpret_cast<float2*>(up + c.up_off + 2 * p) = make_float2((float)(vx / n), (float)(vy / n));
+    float* dst = up + c.up_off + 2 * p0;
+    if (nj == 4 && ((c.up_off + 2 * p0) & 3) == 0) {
+      __stcs(reinterpret_cast<float4*>(dst), make_float4(o[0], o[1], o[2], o[3]));
+      __stcs(reinterpret_cast<float4*>(dst) + 1, make_float4(o[4], o[5], o[6], o[7]));
+    } else {
+      for (int k = 0; k < nj; ++k) *reinterpret_cast<float2*>(dst + 2 * k) = make_float2(o[2 * k], o[2 * k + 1]);
+    }
   }
   if (lat) {
     // numpy.linspace(start, stop, num): start + k * ((stop - start) / (num - 1)), last sample = stop exactly
     const double x0 = (-c.W / 2.0) - (c.cx - (c.W / 2.0)), x1 = (c.W / 2.0) - (c.cx - (c.W / 2.0));
     const double y0 = (-c.H / 2.0) - (c.cy - (c.H / 2.0)), y1 = (c.H / 2.0) - (c.cy - (c.H / 2.0));
-    const double dx = c.W == 1 ? x0 : (j == c.W - 1 ? x1 : (double)j * ((x1 - x0) / (double)(c.W - 1)) + x0);
+    const double sx = c.W == 1 ? 0.0 : (x1 - x0) / (double)(c.W - 1);
     const double dy = c.H == 1 ? y0 : (i == c.H - 1 ? y1 : (double)i * ((y1 - y0) / (double)(c.H - 1)) + y0);
-    const double x = dx / c.f, y = dy / c.f;
-    const double xw = x * c.cr - y * c.sr;
-    const double yw = x * c.ce * c.sr + y * c.ce * c.cr - c.se;
-    const double zw = x * c.se * c.sr + y * c.se * c.cr + c.ce;
-    lat[c.lat_off + p] = (float)(-atan2(yw, sqrt(xw * xw + zw * zw)) / 3.14159265358979323846 * 180.0);
+    const double y = dy / c.f, rf = 1.0 / c.f;
+    // world ray = R_elevation R_roll (x, y, 1):  xw = x cr - y sr;  yw = x ce sr + y ce cr - se;  zw = x se sr + y se cr + ce
+    const double bx = -y * c.sr, by = y * c.ce * c.cr - c.se, bz = y * c.se * c.cr + c.ce;
+    const double ax = c.cr, ay = c.ce * c.sr, az = c.se * c.sr;
+    float o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int j = min(j0 + k, c.W - 1);
+      const double dx = j == c.W - 1 ? (c.W == 1 ? x0 : x1) : fma((double)j, sx, x0);
+      const double x = dx * rf;
+      const float xw = (float)fma(x, ax, bx), yw = (float)fma(x, ay, by), zw = (float)fma(x, az, bz);
+      o[k] = -fast_atan2_deg(yw, sqrtf(fmaf(xw, xw, zw * zw)));
+    }
+    float* dst = lat + c.lat_off + p0;
+    if (nj == 4 && ((c.lat_off + p0) & 3) == 0) __stcs(reinterpret_cast<float4*>(dst), make_float4(o[0], o[1], o[2], o[3]));
+    else for (int k = 0; k < nj; ++k) dst[k] = o[k];
   }
+}
+
+// =====================================================================================================
+// ResizeTransform.apply_image as a stand-alone device transform (perspectivefields.py:34-67; `model.aug.apply_image`).
+//   uint8: Pillow's two-pass antialiased triangle filter, integer arithmetic, bit-exact (same tables / rounding as
+//          preprocess_kernel, arbitrary target size): horizontal pass [H,W,3] -> [H,new_w,3], vertical pass -> [new_h,new_w,3].
+__global__ void __launch_bounds__(256) resize_u8_h_kernel(const unsigned char* __restrict__ src, int H, int W, int OW, const int* __restrict__ bounds,
+                                                          const int* __restrict__ coeffs, int ks, unsigned char* __restrict__ dst) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)H * OW) return;
+  const int y = (int)(i / OW), x = (int)(i - (long long)y * OW);
+  const int xmin = bounds[2 * x], xn = bounds[2 * x + 1];
+  const int* k = coeffs + (long long)x * ks;
+  const unsigned char* row = src + ((long long)y * W + xmin) * 3;
+  int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
+  for (int t = 0; t < xn; ++t) { const int kk = k[t]; a0 += row[3 * t] * kk; a1 += row[3 * t + 1] * kk; a2 += row[3 * t + 2] * kk; }
+  unsigned char* d = dst + i * 3;
+  d[0] = (unsigned char)min(max(a0 >> kPrecisionBits, 0), 255);
+  d[1] = (unsigned char)min(max(a1 >> kPrecisionBits, 0), 255);
+  d[2] = (unsigned char)min(max(a2 >> kPrecisionBits, 0), 255);
+}
+__global__ void __launch_bounds__(256) resize_u8_v_kernel(const unsigned char* __restrict__ src, int H, int OW, int OH, const int* __restrict__ bounds,
+                                                          const int* __restrict__ coeffs, int ks, unsigned char* __restrict__ dst) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)OH * OW) return;
+  const int y = (int)(i / OW), x = (int)(i - (long long)y * OW);
+  const int ymin = bounds[2 * y], yn = bounds[2 * y + 1];
+  const int* k = coeffs + (long long)y * ks;
+  int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
+  for (int t = 0; t < yn; ++t) {
+    const int kk = k[t];
+    const unsigned char* s = src + ((long long)(ymin + t) * OW + x) * 3;
+    a0 += s[0] * kk; a1 += s[1] * kk; a2 += s[2] * kk;
+  }
+  unsigned char* d = dst + i * 3;
+  d[0] = (unsigned char)min(max(a0 >> kPrecisionBits, 0), 255);
+  d[1] = (unsigned char)min(max(a1 >> kPrecisionBits, 0), 255);
+  d[2] = (unsigned char)min(max(a2 >> kPrecisionBits, 0), 255);
+  (void)H;
+}
+//   float32: F.interpolate(mode="bilinear", align_corners=False) without antialias (ATen upsample_bilinear2d: scale = in / out,
+//          src = scale * (dst + 0.5) - 0.5 clamped at 0, i1 = i0 + (i0 < in - 1)); HWC with C channels.  Also the cv2.resize
+//          (INTER_LINEAR) of the visualisation hand-off (demo/demo.py:41-51), which uses the same sampling positions.
+__global__ void __launch_bounds__(256) resize_f32_kernel(const float* __restrict__ src, int H, int W, int C, int OH, int OW, float* __restrict__ dst) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)OH * OW * C) return;
+  const int c = (int)(i % C);
+  const long long pix = i / C;
+  const int x = (int)(pix % OW), y = (int)(pix / OW);
+  const float sch = (float)H / (float)OH, scw = (float)W / (float)OW;
+  const float sy = fmaxf(sch * ((float)y + 0.5f) - 0.5f, 0.f), sx = fmaxf(scw * ((float)x + 0.5f) - 0.5f, 0.f);
+  const int y0 = min((int)sy, H - 1), x0 = min((int)sx, W - 1);
+  const int y1 = y0 + (y0 < H - 1), x1 = x0 + (x0 < W - 1);
+  const float ly = sy - (float)y0, lx = sx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
+  const float v00 = __ldg(src + ((long long)y0 * W + x0) * C + c), v01 = __ldg(src + ((long long)y0 * W + x1) * C + c);
+  const float v10 = __ldg(src + ((long long)y1 * W + x0) * C + c), v11 = __ldg(src + ((long long)y1 * W + x1) * C + c);
+  dst[i] = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
 }
 
 }  // namespace pf

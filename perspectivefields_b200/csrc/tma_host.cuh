@@ -87,13 +87,7 @@ struct PredTail { const float* w; const float* b; float* out; int nc, mode; };  
 
 template <int BN, int MODE, int KB>
 inline cudaError_t gemm_tma_launch_bn(const TmaMaps& maps, const TmaGemmParams& p, int sm_count, cudaStream_t st, const PredTail* pred) {
-  using Cfg = TmaCfg<BN, MODE, KB>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tma_kernel<BN, MODE, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  using Cfg = TmaCfg<BN, MODE, KB>;   // (the > 48 KB shared-memory opt-in is per device: gemm_tma_configure_device, at pf_create)
   const int tiles_x = MODE == MODE_HALO ? cdiv(p.W, kHtTileW) : 0, tiles_y = MODE == MODE_HALO ? cdiv(p.H, kHtTileH) : 0;
   const long long m_tiles = MODE == MODE_GEMM ? cdiv(p.M, 128) : (long long)p.B * tiles_x * tiles_y;
   const long long total = m_tiles * cdiv(p.N, BN) * p.groups;
@@ -124,16 +118,27 @@ inline cudaError_t gemm_tma_launch_bn(const TmaMaps& maps, const TmaGemmParams& 
   return cudaGetLastError();
 }
 
+// every instantiation the dispatcher below can reach: X(BN, MODE, KB)
+#define PF_TMA_VARIANTS(X)                                                                                                  \
+  X(256, MODE_GEMM, 32) X(224, MODE_GEMM, 32) X(192, MODE_GEMM, 32) X(160, MODE_GEMM, 32) X(128, MODE_GEMM, 32) X(96, MODE_GEMM, 32) \
+  X(64, MODE_GEMM, 32) X(32, MODE_GEMM, 32) X(64, MODE_GEMM, 64) X(32, MODE_GEMM, 64)                                        \
+  X(256, MODE_HALO, 32) X(128, MODE_HALO, 64) X(64, MODE_HALO, 64) X(32, MODE_HALO, 64)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute: called once for every device an engine is
+// created on (pf_create) -- not behind a process-wide flag.
+inline cudaError_t gemm_tma_configure_device() {
+  cudaError_t e = cudaSuccess;
+#define PF_TMA_CFG(BN_, MODE_, KB_)                                                                                          \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tma_kernel<BN_, MODE_, KB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, TmaCfg<BN_, MODE_, KB_>::kSmemBytes);
+  PF_TMA_VARIANTS(PF_TMA_CFG)
+#undef PF_TMA_CFG
+  return e;
+}
+
 inline cudaError_t gemm_tma_launch(int mode, const TmaMaps& maps, const TmaGemmParams& p, int bn, int kb, int sm_count, cudaStream_t st,
                                    const PredTail* pred = nullptr) {
-#define PF_TMA_CASE(BN_, MODE_, KB_) if (bn == BN_ && kb == KB_) return gemm_tma_launch_bn<BN_, MODE_, KB_>(maps, p, sm_count, st, pred)
-  if (mode == MODE_GEMM) {
-    PF_TMA_CASE(256, MODE_GEMM, 32); PF_TMA_CASE(224, MODE_GEMM, 32); PF_TMA_CASE(192, MODE_GEMM, 32); PF_TMA_CASE(160, MODE_GEMM, 32);
-    PF_TMA_CASE(128, MODE_GEMM, 32); PF_TMA_CASE(96, MODE_GEMM, 32); PF_TMA_CASE(64, MODE_GEMM, 32); PF_TMA_CASE(32, MODE_GEMM, 32);
-    PF_TMA_CASE(64, MODE_GEMM, 64); PF_TMA_CASE(32, MODE_GEMM, 64);
-  } else {
-    PF_TMA_CASE(256, MODE_HALO, 32); PF_TMA_CASE(128, MODE_HALO, 64); PF_TMA_CASE(64, MODE_HALO, 64); PF_TMA_CASE(32, MODE_HALO, 64);
-  }
+#define PF_TMA_CASE(BN_, MODE_, KB_) if (mode == MODE_ && bn == BN_ && kb == KB_) return gemm_tma_launch_bn<BN_, MODE_, KB_>(maps, p, sm_count, st, pred);
+  PF_TMA_VARIANTS(PF_TMA_CASE)
 #undef PF_TMA_CASE
   return cudaErrorInvalidValue;
 }

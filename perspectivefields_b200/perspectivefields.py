@@ -45,6 +45,9 @@ class _Engine:
             _native.check(self.L.pf_set_weight(self.handle, name.encode(), d.data_ptr(), d.numel(), dt))
         _native.check(self.L.pf_finalize(self.handle))
         self.workspace = None
+        self.ws_stream = None      # stream of the last forward that used the workspace
+        self.ws_event = None       # ... and its completion
+        self.decode_only = False
         self.pinned = None
         self.pinned_event = None
         self.dev_blob = None
@@ -61,11 +64,20 @@ class _Engine:
         except Exception:
             pass
 
-    def _workspace(self, n, max_h):
+    def _workspace(self, n, max_h, cur):
+        """Scratch for pf_forward.  The buffer is allocated from torch's caching allocator on the stream of its first use; a
+        caller that switches streams between calls is kept safe by stream-ordering the hand-over: the new stream waits for the
+        last forward that used the workspace (``ws_event``), and a workspace that is replaced is marked as used by that stream
+        (``record_stream``) so that its block is not recycled under a forward still running there."""
         need = _native.check(self.L.pf_workspace_bytes(self.handle, n, max_h))
+        if self.ws_event is not None and self.ws_stream is not None and self.ws_stream != cur:
+            cur.wait_event(self.ws_event)
         if self.workspace is None or self.workspace.numel() < need:
+            if self.workspace is not None and self.ws_stream is not None:
+                self.workspace.record_stream(self.ws_stream)
             self.workspace = None
             self.workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+        self.ws_stream = cur
         return self.workspace
 
     def stage_images(self, imgs):
@@ -113,15 +125,17 @@ class _Engine:
         l_off = np.zeros(n, np.int64)
         np.cumsum(2 * hw[:-1], out=g_off[1:])
         np.cumsum(hw[:-1], out=l_off[1:])
+        cur = torch.cuda.current_stream(dev)
+        gc_, lc_ = (2, 1) if self.decode_only else (self.gravity_classes, self.latitude_classes)
         out = {
-            "pred_gravity": torch.empty((n, self.gravity_classes, _NET, _NET), dtype=torch.float32, device=dev),
-            "pred_latitude": torch.empty((n, self.latitude_classes, _NET, _NET), dtype=torch.float32, device=dev),
+            "pred_gravity": torch.empty((n, gc_, _NET, _NET), dtype=torch.float32, device=dev),
+            "pred_latitude": torch.empty((n, lc_, _NET, _NET), dtype=torch.float32, device=dev),
             "gravity_original": torch.empty(int(2 * hw.sum()), dtype=torch.float32, device=dev),
             "latitude_original": torch.empty(int(hw.sum()), dtype=torch.float32, device=dev),
             "params": torch.empty((n, 8), dtype=torch.float32, device=dev),
             "g_off": g_off, "l_off": l_off, "h": h, "w": w,
         }
-        ws = self._workspace(n, int(h.max()))
+        ws = self._workspace(n, int(h.max()), cur)
         bt = _native.pf_batch()
         bt.n = n
         i64p, i32p = ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int32)
@@ -136,31 +150,58 @@ class _Engine:
         bt.gravity_original, bt.gravity_original_offset = out["gravity_original"].data_ptr(), g_off.ctypes.data_as(i64p)
         bt.latitude_original, bt.latitude_original_offset = out["latitude_original"].data_ptr(), l_off.ctypes.data_as(i64p)
         bt.params = out["params"].data_ptr()
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        _native.check(self.L.pf_forward(self.handle, ctypes.byref(bt), ws.data_ptr(), ws.numel(), stream))
+        _native.check(self.L.pf_forward(self.handle, ctypes.byref(bt), ws.data_ptr(), ws.numel(), cur.cuda_stream))
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self.ws_event = ev
         if blob is not None and self.staged_slot is not None and self.dev_blob is not None and blob is self.dev_blob[self.staged_slot]:
-            ev = torch.cuda.Event()
-            ev.record()
             self.blob_free[self.staged_slot] = ev   # stage_images may overwrite this device blob once the forward has read it
         return out
 
 
 class ResizeTransform:
-    """The ``aug`` attribute of the reference class (perspectivefields.py:16-67, built at :155): target size and PIL filter of
-    the input resize.  Here the resize itself runs inside the CUDA pre-process (Pillow-exact integer arithmetic,
-    csrc/prepost.cuh:preprocess_kernel), so the object only carries the parameters; ``apply_image`` points there."""
+    """The ``aug`` attribute of the reference class (perspectivefields.py:16-67, built at :155).  ``apply_image`` keeps the
+    reference's contract -- numpy HWC in, numpy HWC out, uint8 through Pillow's antialiased bilinear resampler (bit-exact
+    integer restatement, csrc/prepost.cuh: the same arithmetic ``inference`` uses inside its fused pre-process), any other
+    dtype through ``F.interpolate(mode="bilinear", align_corners=False)`` -- but the arithmetic runs on the GPU
+    (``pf_op_resize_u8`` / ``pf_op_resize_f32``).  Only the bilinear filter exists here (the one the path uses)."""
 
     def __init__(self, new_h, new_w, interp=None):
         self.new_h, self.new_w = new_h, new_w
         self.interp = 2 if interp is None else interp          # PIL.Image.BILINEAR == 2
 
     def apply_image(self, img, interp=None):
-        raise NotImplementedError("the 320x320 resize is part of the CUDA pre-process of PerspectiveFields.inference / "
-                                  "inference_batch; it is not available as a separate host-side transform")
+        img = np.asarray(img)
+        assert len(img.shape) <= 4
+        method = self.interp if interp is None else interp
+        if method != 2:
+            raise NotImplementedError("perspectivefields_b200 implements the BILINEAR resize of the inference path only")
+        if not torch.cuda.is_available():
+            raise RuntimeError("perspectivefields_b200 has no CPU path: ResizeTransform.apply_image needs a CUDA device")
+        L = _native.lib()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        if img.dtype == np.uint8:
+            if img.ndim != 3 or img.shape[2] != 3:
+                raise TypeError("uint8 images must be (H, W, 3); got %s" % (img.shape,))
+            src = torch.from_numpy(np.ascontiguousarray(img)).to(dev)
+            out = torch.empty((self.new_h, self.new_w, 3), dtype=torch.uint8, device=dev)
+            _native.check(L.pf_op_resize_u8(src.data_ptr(), img.shape[0], img.shape[1], self.new_h, self.new_w, out.data_ptr(), stream))
+            return out.cpu().numpy()
+        if img.ndim not in (2, 3):
+            raise TypeError("float images must be (H, W) or (H, W, C); got %s" % (img.shape,))
+        c = 1 if img.ndim == 2 else img.shape[2]
+        src = torch.from_numpy(np.ascontiguousarray(img, dtype=np.float32)).to(dev)
+        out = torch.empty((self.new_h, self.new_w) + img.shape[2:], dtype=torch.float32, device=dev)
+        _native.check(L.pf_op_resize_f32(src.data_ptr(), img.shape[0], img.shape[1], c, self.new_h, self.new_w, out.data_ptr(), stream))
+        return out.cpu().numpy().astype(img.dtype, copy=False)
 
 
 class PerspectiveFields(nn.Module):
-    def __init__(self, version="Paramnet-360Cities-edina-centered"):
+    def __init__(self, version="Paramnet-360Cities-edina-centered", logits=True):
+        """``logits=False`` (classification variant only; NOT the reference's behaviour): ``pred_gravity`` /
+        ``pred_latitude`` hold the decoded fields ([2,320,320] up-vectors, [1,320,320] degrees) instead of the 73 / 180 raw logits,
+        which are then never written (engine option "decode_only"); the ``*_original`` entries are unchanged."""
         super().__init__()
         zoo = model_zoo[version]  # KeyError for unknown versions, like the reference (perspectivefields.py:127)
         self.version = version
@@ -178,6 +219,11 @@ class PerspectiveFields(nn.Module):
         self._ref_state = default_state(version)   # reference-layout weights, host side
         self._engine = None
         self._options = {}
+        self._jpeg = None
+        if not logits:
+            if self._variant["gravity"] != "classification":
+                raise ValueError("logits=False only applies to the classification variant (PersNet-360Cities)")
+            self._options["decode_only"] = 1
         self.training = False
         self._init_weights()
 
@@ -197,9 +243,20 @@ class PerspectiveFields(nn.Module):
             raise RuntimeError("perspectivefields_b200.PerspectiveFields is inference-only: call .eval()")
         return super().train(False)
 
-    def state_dict(self, *args, **kwargs):
-        """The reference's key layout (backbone.*, ll_enc.*, persformer_heads.*, param_net.backbone.*)."""
-        return {k: v.clone() for k, v in self._ref_state.items()}
+    def state_dict(self, *args, destination=None, prefix="", keep_vars=False):
+        """The reference's key layout (backbone.*, ll_enc.*, persformer_heads.*, param_net.backbone.*), with
+        ``nn.Module.state_dict``'s arguments: entries are added to ``destination`` under ``prefix``; ``keep_vars`` returns the
+        stored tensors themselves instead of detached copies."""
+        if args:   # legacy positional form: (destination, prefix, keep_vars)
+            destination = args[0]
+            prefix = args[1] if len(args) > 1 else prefix
+            keep_vars = args[2] if len(args) > 2 else keep_vars
+        if destination is None:
+            import collections
+            destination = collections.OrderedDict()
+        for k, v in self._ref_state.items():
+            destination[prefix + k] = v if keep_vars else v.detach().clone()
+        return destination
 
     def load_state_dict(self, state_dict, strict=True, assign=False):
         missing = [k for k in self._schema if k not in state_dict]
@@ -227,6 +284,9 @@ class PerspectiveFields(nn.Module):
             self.load_state_dict(state_dict["model"], strict=False)
 
     def _drop_engine(self):
+        if self._jpeg is not None and self._engine is not None:
+            self._engine.L.pf_jpeg_destroy(self._jpeg)
+        self._jpeg = None
         if self._engine is not None:
             self._engine.close()
             self._engine = None
@@ -245,6 +305,7 @@ class PerspectiveFields(nn.Module):
             eng.latitude_classes = self._variant["latitude_classes"]
             for k, v in self._options.items():
                 _native.check(eng.L.pf_set_option(eng.handle, k.encode(), v))
+            eng.decode_only = bool(self._options.get("decode_only", 0))
             self._engine = eng
         return self._engine
 
@@ -255,20 +316,92 @@ class PerspectiveFields(nn.Module):
 
     @torch.no_grad()
     def inference_batch(self, img_bgr_list):
+        """perspectivefields.py:207-221.  uint8 (H, W, 3) images take the fused path (one packed upload, Pillow-exact resize +
+        normalise in one kernel); a list containing any other dtype takes the reference's float branch for ALL its members
+        (``ResizeTransform.apply_image`` -> non-antialiased ``F.interpolate``, perspectivefields.py:47-66, on the GPU) and then
+        the ``forward`` entry."""
         imgs = []
+        all_u8 = True
         for im in img_bgr_list:
             im = np.asarray(im)
-            if im.dtype != np.uint8 or im.ndim != 3 or im.shape[2] != 3:
-                raise TypeError("inference expects (H, W, 3) uint8 BGR images; got %s %s" % (im.dtype, im.shape))
+            if im.ndim != 3 or im.shape[2] != 3:
+                raise TypeError("inference expects (H, W, 3) BGR images; got %s %s" % (im.dtype, im.shape))
             if self.input_format == "RGB":
                 im = im[:, :, ::-1]
+            all_u8 = all_u8 and im.dtype == np.uint8
             imgs.append(np.ascontiguousarray(im))
         if not imgs:
             return []
         eng = self._get_engine()
         with torch.cuda.device(eng.device):
+            if not all_u8:
+                inputs = []
+                for im in imgs:
+                    r = self.aug.apply_image(im)
+                    inputs.append({"image": torch.as_tensor(r.astype("float32").transpose(2, 0, 1)), "height": im.shape[0], "width": im.shape[1]})
+                return self.forward(inputs)
             blob, offsets = eng.stage_images(imgs)
             out = eng.forward(len(imgs), [im.shape[0] for im in imgs], [im.shape[1] for im in imgs], blob=blob, offsets=offsets)
+        return self._assemble(out)
+
+    # ---- blob-level access for the multi-GPU gather (dist.py): the five output blobs of a batch move as whole buffers ----
+    @torch.no_grad()
+    def infer_raw(self, img_bgr_list):
+        """``inference_batch`` up to (not including) the per-image views: returns the engine's batch outputs
+        (``pred_gravity [n,Cg,320,320]``, ``pred_latitude``, flat ``gravity_original`` / ``latitude_original`` blobs, ``params [n,8]``)
+        plus the host-side offsets / sizes ``assemble_raw`` needs.  uint8 images only."""
+        imgs = []
+        for im in img_bgr_list:
+            im = np.asarray(im)
+            if im.dtype != np.uint8 or im.ndim != 3 or im.shape[2] != 3:
+                raise TypeError("infer_raw expects (H, W, 3) uint8 BGR images; got %s %s" % (im.dtype, im.shape))
+            if self.input_format == "RGB":
+                im = im[:, :, ::-1]
+            imgs.append(np.ascontiguousarray(im))
+        eng = self._get_engine()
+        with torch.cuda.device(eng.device):
+            blob, offsets = eng.stage_images(imgs)
+            return eng.forward(len(imgs), [im.shape[0] for im in imgs], [im.shape[1] for im in imgs], blob=blob, offsets=offsets)
+
+    def assemble_raw(self, raw):
+        return self._assemble(raw)
+
+    def out_classes(self):
+        """Channel counts of ``pred_gravity`` / ``pred_latitude`` as returned (2 / 1 in "decode_only" mode)."""
+        if self._options.get("decode_only", 0):
+            return (2, 1)
+        return (self._variant["gravity_classes"], self._variant["latitude_classes"])
+
+    @torch.no_grad()
+    def inference_batch_encoded(self, jpeg_list, max_threads=0):
+        """Decode front-end: a list of JPEG byte strings (what ``cv2.imread`` would read from disk,
+        demo/demo.py:151) is decoded on the GPU (nvJPEG, BGR interleaved) straight into the device blob the fused pre-process
+        reads; no host-side pixel buffer exists.  Returns the same ``list[dict]`` as ``inference_batch``."""
+        if self.input_format != "BGR":
+            raise NotImplementedError("the decode front-end writes BGR (the reference's INPUT.FORMAT)")
+        if not jpeg_list:
+            return []
+        eng = self._get_engine()
+        L = eng.L
+        with torch.cuda.device(eng.device):
+            if self._jpeg is None:
+                self._jpeg = ctypes.c_void_p()
+                _native.check(L.pf_jpeg_create(eng.device.index, max_threads, ctypes.byref(self._jpeg)))
+            n = len(jpeg_list)
+            bufs = [np.frombuffer(b, dtype=np.uint8) for b in jpeg_list]
+            hs, ws = (ctypes.c_int32 * n)(), (ctypes.c_int32 * n)()
+            for i, b in enumerate(bufs):
+                h1, w1 = ctypes.c_int32(), ctypes.c_int32()
+                _native.check(L.pf_jpeg_info(self._jpeg, b.ctypes.data, b.size, ctypes.byref(h1), ctypes.byref(w1)))
+                hs[i], ws[i] = h1.value, w1.value
+            sizes = [hs[i] * ws[i] * 3 for i in range(n)]
+            offs = (ctypes.c_int64 * n)(*np.concatenate([[0], np.cumsum(sizes[:-1])]).astype(np.int64).tolist())
+            blob = torch.empty(int(sum(sizes)), dtype=torch.uint8, device=eng.device)
+            ptrs = (ctypes.c_void_p * n)(*[b.ctypes.data for b in bufs])
+            lens = (ctypes.c_int64 * n)(*[b.size for b in bufs])
+            stream = torch.cuda.current_stream(eng.device).cuda_stream
+            _native.check(L.pf_jpeg_decode_batch(self._jpeg, n, ptrs, lens, hs, ws, blob.data_ptr(), offs, stream))
+            out = eng.forward(n, list(hs), list(ws), blob=blob, offsets=np.asarray(list(offs), np.int64))
         return self._assemble(out)
 
     @torch.no_grad()
@@ -317,6 +450,7 @@ class PerspectiveFields(nn.Module):
         eng = self._get_engine()
         _native.check(eng.L.pf_set_option(eng.handle, name.encode(), int(value)))
         self._options[name] = int(value)
+        eng.decode_only = bool(self._options.get("decode_only", 0))
 
     # ------------------------------------------------------------------------------------------ test hooks
     def debug_taps(self, enable=True):

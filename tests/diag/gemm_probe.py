@@ -1,4 +1,4 @@
-"""GPU: time (and let ncu capture) single GEMM-engine launches of chosen shapes through pf_op_conv_gemm engine 3."""
+"""GPU: time (and let ncu capture) single GEMM-engine launches of chosen shapes through pf_op_conv_gemm."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -17,12 +17,12 @@ for (M, N, K) in shapes:
     ACT = int(os.environ.get('PF_PROBE_ACT', '0'))
     for eng in (3,):
         for _ in range(2):
-            _native.check(L.pf_op_conv_gemm(x.data_ptr(), 1, 1, M, K, hi.data_ptr(), lo.data_ptr(), b.data_ptr(), N, 1, 1, 1, 0, 0, ACT, None, 0, y.data_ptr(), eng, U.stream_ptr()))
+            _native.check(L.pf_op_conv_gemm(x.data_ptr(), 1, 1, M, K, hi.data_ptr(), lo.data_ptr(), b.data_ptr(), N, 1, 1, 1, 0, 0, ACT, None, 0, y.data_ptr(), U.stream_ptr()))
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        # engine 3's test entry splits the input and synchronises inside: time includes the split kernel; ncu isolates the GEMM
+        # the test entry splits the input and synchronises inside: time includes the split kernel; ncu isolates the GEMM
         e0.record()
         for _ in range(5):
-            _native.check(L.pf_op_conv_gemm(x.data_ptr(), 1, 1, M, K, hi.data_ptr(), lo.data_ptr(), b.data_ptr(), N, 1, 1, 1, 0, 0, ACT, None, 0, y.data_ptr(), eng, U.stream_ptr()))
+            _native.check(L.pf_op_conv_gemm(x.data_ptr(), 1, 1, M, K, hi.data_ptr(), lo.data_ptr(), b.data_ptr(), N, 1, 1, 1, 0, 0, ACT, None, 0, y.data_ptr(), U.stream_ptr()))
         e1.record(); torch.cuda.synchronize()
         print(f"M{M} N{N} K{K} engine {eng}: {e0.elapsed_time(e1)/5*1000:.1f} us per call (incl. split + sync)", flush=True)

@@ -29,3 +29,28 @@ def test_result_keys_all_versions():
     for ver, info in m["versions"].items():
         n = {"ParamNet": 12, "ParamNetConvNextRegress": 11, None: 5}[VARIANTS[ver]["param_net"]]
         assert all(len(k) == n for k in info["keys"])
+
+
+def test_classification_decoded_fields_match_reference_golden_on_stable_pixels():
+    """pred_gravity_original / pred_latitude_original of PersNet-360Cities against the unmodified reference's stored outputs:
+    argmax is discontinuous in the logits, so the comparison is restricted to pixels whose four bilinear source taps all have
+    an unambiguous argmax (tests/pf_test_util.py:stable_mask) -- and is tight (1e-4) there."""
+    import torch
+
+    import pf_test_util as U
+    from golden_util import load_golden
+
+    version = "PersNet-360Cities"
+    sd = wg.synth_state_dict(version, 0)
+    out = om.inference_batch(sd, version, golden_images())
+    m, g = load_golden(version)
+    st, lst = m["stride"], m["logit_stride"]
+    for i, res in enumerate(out):
+        h, w = res["pred_latitude_original"].shape
+        for key, okey, scale in (("pred_gravity", "pred_gravity_original", 1.0), ("pred_latitude", "pred_latitude_original", 90.0)):
+            err = float(abs(res[key][..., ::lst, ::lst].numpy() - g[f"{i}/{key}"]).max())
+            stable = U.stable_mask(res[key], max(err, 1e-6), h, w)[::st, ::st]
+            assert stable.float().mean() > 0.8
+            d = (res[okey][..., ::st, ::st] - torch.from_numpy(g[f"{i}/{okey}"])).abs()
+            d = d.amax(0) if d.ndim == 3 else d
+            assert d[stable].max().item() / scale < 1e-4, (i, okey)
