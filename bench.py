@@ -59,7 +59,7 @@ def parse():
     ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: the configuration's)")
     ap.add_argument("--cpu-sample", type=int, default=8, help="images in the bounded CPU-baseline sample")
-    ap.add_argument("--micro-batch", type=int, default=16, help="images per micro-batch of the gather-inclusive multi-GPU leg")
+    ap.add_argument("--micro-batch", type=int, default=32, help="images per micro-batch of the gather-inclusive multi-GPU leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile-passes", action="store_true", help="skip the roofline / per-kernel passes (A/B timing runs)")
     return ap.parse_args()
@@ -359,7 +359,7 @@ class Bench:
         return max(f0.elapsed_time(f1), wall_ms), h2d_bytes, d2h_bytes
 
 
-def roofline_objects(args, B, prof, prof_ms, ms, per_kernel, heights, widths, peaks):
+def roofline_objects(args, B, prof, prof_ms, ms, per_kernel, heights, widths, peaks, write_peak=None):
     peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16, kernel timed inside a long step)" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
     traffic, traffic_src = None, None
@@ -394,10 +394,10 @@ def roofline_objects(args, B, prof, prof_ms, ms, per_kernel, heights, widths, pe
         "per_engine": {names[c].split(" (")[0]: {"ms_per_step": prof[3 * c] / args.steps, "tflops": prof[3 * c + 1] / (prof[3 * c] / 1000.0) / 1e12,
                                                  "launches_per_step": prof[3 * c + 2] / args.steps} for c in cfgs},
     }
-    return roofline, post_roofline(per_kernel, heights, widths, peaks)
+    return roofline, post_roofline(per_kernel, heights, widths, peaks, write_peak)
 
 
-def post_roofline(per_kernel, heights, widths, peaks):
+def post_roofline(per_kernel, heights, widths, peaks, write_peak=None):
     """HBM-bound tail of the path (the "decode-head" HBM roofline applies to the write-out stage): resample of the
     three 320x320 fields to the original sizes + normalise / asin.  Algorithmic bytes = 4*(3*320*320 read + 3*H*W written) per image."""
     pk = per_kernel.get("postprocess_kernel")
@@ -406,10 +406,18 @@ def post_roofline(per_kernel, heights, widths, peaks):
     post_bytes = sum(4 * (3 * 320 * 320 + 3 * int(h_) * int(w_)) for h_, w_ in zip(heights, widths))
     hbm_peak = peaks.get("hbm_gbs") or 6500.0
     gbps = post_bytes / (pk["ms_per_step"] / 1000.0) / 1e9
-    return {"bound": "hbm", "kernel": "postprocess_kernel (bilinear resample to (H,W) + F.normalize / asin, all images of the batch in one launch)",
-            "achieved": gbps, "peak": hbm_peak, "unit": "GB/s", "frac": gbps / hbm_peak, "bytes_per_step": post_bytes,
-            "ms_per_step": pk["ms_per_step"], "size": f"{widths[0]}x{heights[0]} x {len(heights)}",
-            "note": "in-pipeline CUDA-event time of the per-kernel pass (includes ~2-4 us of event overhead per launch)"}
+    r = {"bound": "hbm", "kernel": "postprocess_kernel (bilinear resample to (H,W) + F.normalize / asin, all images of the batch in one launch)",
+         "achieved": gbps, "peak": hbm_peak, "unit": "GB/s", "frac": gbps / hbm_peak, "bytes_per_step": post_bytes,
+         "ms_per_step": pk["ms_per_step"], "size": f"{widths[0]}x{heights[0]} x {len(heights)}",
+         "note": "in-pipeline CUDA-event time of the per-kernel pass (includes ~2-4 us of event overhead per launch); `peak` is the measured "
+                 "COPY bandwidth (read + write bytes); the kernel's traffic is 75 % writes, and `write_peak` is this GPU's measured write-only "
+                 "bandwidth (torch fill_ of 1 GiB), the bound that applies to them"}
+    if write_peak:
+        wbytes = sum(12 * int(h_) * int(w_) for h_, w_ in zip(heights, widths))
+        r["write_peak"] = write_peak
+        r["write_gbs"] = wbytes / (pk["ms_per_step"] / 1000.0) / 1e9
+        r["frac_of_write_peak"] = r["write_gbs"] / write_peak
+    return r
 
 
 def load_peaks():
@@ -420,8 +428,34 @@ def load_peaks():
         return {}
 
 
-def camera_fields_roofline(dev, heights, widths, peaks, steps):
-    """Row f-1 (camera parameters -> dense fields): 12 B of stores per pixel, timed with CUDA events around `steps` launches."""
+def measured_write_peak(dev):
+    """Pure-WRITE bandwidth of this GPU's HBM (GB/s), measured live the way MEASURED_PEAKS.json measures the copy peak: the better
+    of torch ``fill_`` and a 16-byte streaming-store kernel (pf_op_fill_stream) over 1 GiB, best of 4 each, CUDA events.  The copy peak counts read + write bytes; a kernel that only writes (the
+    post-process / camera-field write-out) cannot exceed this number, which on this pool's B200s is well below half the copy peak."""
+    import torch
+
+    from perspectivefields_b200 import _native
+
+    L = _native.lib()
+    a = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    best = 0.0
+    for fn in (lambda: a.fill_(3), lambda: _native.check(L.pf_op_fill_stream(a.data_ptr(), a.numel() // 4, 1.0, st))):   # torch's fill and 16-byte streaming stores
+        for _ in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            best = max(best, a.numel() / e0.elapsed_time(e1) / 1e6)
+    del a
+    return best
+
+
+def camera_fields_roofline(dev, heights, widths, peaks, steps, write_peak=None):
+    """Row f-1 (camera parameters -> dense fields): 12 B of stores per pixel.  The launch sequence of one call is captured in a
+    CUDA graph and replayed, so that the CUDA-event time is the kernels' (the Python + descriptor build of a call costs more than
+    the kernel at small sizes); falls back to timing back-to-back calls."""
     import torch
 
     from perspectivefields_b200 import panocam
@@ -430,18 +464,38 @@ def camera_fields_roofline(dev, heights, widths, peaks, steps):
     args_ = ([0.8] * n, heights, widths, [0.3] * n, [0.1] * n, [0.02] * n, [-0.03] * n)
     panocam.camera_fields(*args_, device=dev)
     torch.cuda.synchronize(dev)
+    reps = max(steps, 10)
+    how = "CUDA graph replay of one call's launches"
+    try:
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            panocam.camera_fields(*args_, device=dev)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        with torch.cuda.graph(g):
+            out = panocam.camera_fields(*args_, device=dev)
+        run = g.replay
+    except Exception as ex:   # capture not possible: time whole calls
+        how = f"back-to-back calls incl. host work ({type(ex).__name__})"
+        run = lambda: panocam.camera_fields(*args_, device=dev)
+    run()
+    torch.cuda.synchronize(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(steps):
-        out = panocam.camera_fields(*args_, device=dev)
+    for _ in range(reps):
+        run()
     e1.record()
     torch.cuda.synchronize(dev)
-    del out
-    ms = e0.elapsed_time(e1) / steps
+    ms = e0.elapsed_time(e1) / reps
     nbytes = 12 * sum(int(h) * int(w) for h, w in zip(heights, widths))
     hbm_peak = peaks.get("hbm_gbs") or 6500.0
-    return {"kernel": "camera_fields_kernel", "ms": ms, "bytes": nbytes, "achieved": nbytes / ms / 1e6, "peak": hbm_peak, "unit": "GB/s",
-            "frac": nbytes / ms / 1e6 / hbm_peak, "note": "includes the host-side descriptor build and launch of each call (steps back to back)"}
+    r = {"kernel": "camera_fields_kernel", "ms": ms, "bytes": nbytes, "achieved": nbytes / ms / 1e6, "peak": hbm_peak, "unit": "GB/s",
+         "frac": nbytes / ms / 1e6 / hbm_peak, "timing": how}
+    if write_peak:
+        r["write_peak"] = write_peak
+        r["frac_of_write_peak"] = nbytes / ms / 1e6 / write_peak
+    return r
 
 
 def gather_leg(b, imgs_rank, steps, warmup, micro_batch):
@@ -506,6 +560,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
     extra = {}
+    write_peak = measured_write_peak(dev)
+    extra["hbm_write_gbs_measured"] = write_peak
 
     b = Bench(args, cfg, dev, rank, world)
     imgs = make_images(cfg, B, 1000 + rank)   # each rank owns its shard of the global batch
@@ -524,7 +580,7 @@ def main():
     per_kernel = {}
     if not args.no_profile_passes:
         prof, prof_ms, per_kernel = b.profile_passes(staged, args.steps)
-        roofline, roofline_post = roofline_objects(args, B, prof, prof_ms, ms, per_kernel, staged[2], staged[3], peaks)
+        roofline, roofline_post = roofline_objects(args, B, prof, prof_ms, ms, per_kernel, staged[2], staged[3], peaks, write_peak)
     del staged
 
     # ---------------- leg 2: end to end through the public API, host arrays in, results read back to the host -----
@@ -545,18 +601,18 @@ def main():
             row = {"size": f"{w}x{h}", "batch": B, "images_per_s": B * args.steps / (ms_r / 1000.0), "ms_per_step": ms_r / args.steps}
             if not args.no_profile_passes:
                 _, _, pk = b.profile_passes(st, args.steps)
-                row["roofline_post"] = post_roofline(pk, st[2], st[3], peaks)
+                row["roofline_post"] = post_roofline(pk, st[2], st[3], peaks, write_peak)
                 pre = pk.get("preprocess_kernel")
                 if pre:
                     pre_bytes = B * (3 * h * w + 16 * 320 * 320)
                     row["preprocess"] = {"ms_per_step": pre["ms_per_step"], "bytes_per_step": pre_bytes, "achieved_gbs": pre_bytes / pre["ms_per_step"] / 1e6}
-            row["camera_fields"] = camera_fields_roofline(dev, [h] * B, [w] * B, peaks, max(args.steps, 5))
+            row["camera_fields"] = camera_fields_roofline(dev, [h] * B, [w] * B, peaks, max(args.steps, 5), write_peak)
             del st
             sweep.append(row)
         extra["resolution_sweep"] = sweep
     elif rank == 0 and world == 1:
         h, w = cfg["sizes"][0]
-        extra["roofline_camera_fields"] = camera_fields_roofline(dev, [h] * B, [w] * B, peaks, max(args.steps, 5))
+        extra["roofline_camera_fields"] = camera_fields_roofline(dev, [h] * B, [w] * B, peaks, max(args.steps, 5), write_peak)
 
     # ---------------- P360: the classification variant without logits (option "decode_only") -------------------------------
     if args.config == "P360":

@@ -185,6 +185,9 @@ int pf_op_preprocess(const uint8_t* img_dev, int H, int W, const float* mean3, c
  *   float32 (:47-66): F.interpolate(mode="bilinear", align_corners=False), no antialias. */
 int pf_op_resize_u8(const uint8_t* img_dev, int H, int W, int new_h, int new_w, uint8_t* out_dev, void* stream);   /* C = 3 */
 int pf_op_resize_f32(const float* img_dev, int H, int W, int C, int new_h, int new_w, float* out_dev, void* stream);
+/* write-only bandwidth probe: fills dst[numel] (numel % 4 == 0, 16-byte aligned) with 16-byte streaming stores (bench.py measures
+ * the store roofline of the write-out kernels with it). */
+int pf_op_fill_stream(float* dst, int64_t numel, float value, void* stream);
 /* argmax over channels + bin decode of NCHW logits [B,NC,HW] (gravity_head.py:243-244 + utils/utils.py:114-130 when
  * is_gravity, field [B,2,HW]; latitude_head.py:205-208 + utils/utils.py:148-162 otherwise, field [B,1,HW] in degrees). */
 int pf_op_argmax_decode(const float* logits, float* field, int B, int HW, int NC, int is_gravity, void* stream);

@@ -117,6 +117,7 @@ def lib():
         "pf_op_resize_u8": (i32, [vp, i32, i32, i32, i32, vp, vp]),
         "pf_op_resize_f32": (i32, [vp, i32, i32, i32, i32, i32, vp, vp]),
         "pf_op_argmax_decode": (i32, [vp, vp, i32, i32, i32, i32, vp]),
+        "pf_op_fill_stream": (i32, [vp, i64, f32, vp]),
         "pf_op_pred_argmax_decode": (i32, [vp, i32, i32, vp, vp, vp, i32, i32, i32, i32, vp]),
         "pf_op_postprocess": (i32, [vp, vp, i32, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), vp, ctypes.POINTER(i64), vp,
                                     ctypes.POINTER(i64), i32, vp]),
@@ -150,7 +151,7 @@ EXPORTS = ["pf_abi_version", "pf_last_error", "pf_kernel_launch_count", "pf_crea
            "pf_debug_copy", "pf_camera_fields", "pf_comm_unique_id", "pf_comm_create", "pf_comm_destroy", "pf_gather",
            "pf_jpeg_create", "pf_jpeg_destroy", "pf_jpeg_info", "pf_jpeg_decode_batch",
            "pf_op_conv_gemm", "pf_op_layernorm", "pf_op_attention", "pf_op_attention_mma", "pf_op_dwconv3x3_gelu", "pf_op_dwconv7x7",
-           "pf_op_upsample2x", "pf_op_preprocess", "pf_op_resize_u8", "pf_op_resize_f32", "pf_op_argmax_decode",
+           "pf_op_upsample2x", "pf_op_preprocess", "pf_op_fill_stream", "pf_op_resize_u8", "pf_op_resize_f32", "pf_op_argmax_decode",
            "pf_op_pred_argmax_decode", "pf_op_postprocess"]
 
 

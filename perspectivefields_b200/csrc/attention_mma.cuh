@@ -32,6 +32,8 @@ __global__ void __launch_bounds__(kAmThreads) attention_mma_kernel(const float* 
                                                                    float* __restrict__ out,
                                                                    __nv_bfloat16* __restrict__ shi, __nv_bfloat16* __restrict__ slo, int N, int C,
                                                                    int tiles_per_block) {
+  pdl_wait();
+  pdl_launch();
   extern __shared__ __align__(128) unsigned char sm_raw[];
   const uint32_t sK_hi = smem_u32(sm_raw), sK_lo = sK_hi + kAmPlane, sV_hi = sK_lo + kAmPlane, sV_lo = sV_hi + kAmPlane;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -210,9 +212,8 @@ inline cudaError_t attention_mma_launch(const float* q, const float* kv, float* 
   int tpb = (tiles * heads * B) / 400;
   tpb = tpb < 1 ? 1 : (tpb > tiles ? tiles : tpb);
   dim3 grid(cdiv(tiles, tpb), heads, B);
-  if (qs.hi) attention_mma_kernel<true><<<grid, kAmThreads, kAmSmem, st>>>(nullptr, nullptr, qs.hi, qs.lo, kvs.hi, kvs.lo, out, sp.hi, sp.lo, N, C, tpb);
-  else attention_mma_kernel<false><<<grid, kAmThreads, kAmSmem, st>>>(q, kv, nullptr, nullptr, nullptr, nullptr, out, sp.hi, sp.lo, N, C, tpb);
-  return cudaGetLastError();
+  if (qs.hi) return launch_pdl(attention_mma_kernel<true>, grid, dim3(kAmThreads), kAmSmem, st, nullptr, nullptr, qs.hi, qs.lo, kvs.hi, kvs.lo, out, sp.hi, sp.lo, N, C, tpb);
+  return launch_pdl(attention_mma_kernel<false>, grid, dim3(kAmThreads), kAmSmem, st, q, kv, nullptr, nullptr, nullptr, nullptr, out, sp.hi, sp.lo, N, C, tpb);
 }
 
 }  // namespace pf

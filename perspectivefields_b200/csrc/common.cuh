@@ -11,6 +11,31 @@ constexpr int kNet = 320;  // network working resolution (every shipped config: 
 __host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline long long cdivl(long long a, long long b) { return (a + b - 1) / b; }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// The forward graph is ~450 dependent launches of 10-60 us kernels.  Kernels launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization may begin (block scheduling, prologue: barrier init, TMEM allocation,
+// descriptor prefetch) while the previous kernel of the stream is still draining; pdl_wait() (griddepcontrol.wait) then blocks
+// until that kernel has completed and its memory is visible -- every kernel launched that way calls it before its first global
+// access.  It is a no-op for ordinary launches.  pdl_launch() lets the NEXT kernel's launch proceed as early as possible.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool& pdl_enabled() {   // set per pf_forward call from the engine option "pdl"
+  static thread_local bool on = false;
+  return on;
+}
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ---------------------------------------------------------------- bf16 hi/lo split of an fp32 value
 // x ~= hi + lo with hi = bf16(x), lo = bf16(x - hi): 16 significant bits.  A product a*b is then
 // evaluated on the tensor cores as a_hi*b_hi + a_lo*b_hi + a_hi*b_lo (fp32 accumulate), relative error

@@ -53,6 +53,12 @@ struct TmaGemmParams {
   // bilinear x2 upsample in front of it (weights.py:_compose_up2_conv3): chunk ph, low-res pixel (y, x) -> pixel
   // (2y + ph/2, 2x + ph%2) of the 2H x 2W output, 32 channels.  C / S / the prediction tail are addressed on that grid.
   int phase4;
+  // timing experiments (tests/diag/gemm_probe.py, env PF_GEMM_DBG; 0 in production): bit 0 = epilogue without global stores,
+  // bit 1 = producer re-arms the stages without loading (operands stay whatever the first pass loaded), bit 2 = no MMAs issued,
+  // bit 3 = epilogue without the TMEM read, bit 4 = no fence.proxy.async, bit 5 = no bulk wait, bit 6 = no bias staging,
+  // bit 7 = the epilogue only waits and releases the accumulator, bit 8 = producer / MMA warps poll their barriers
+  // (test_wait) instead of the suspending try_wait, bit 9 = the epilogue warps too.  Results are then meaningless; only the kernel duration is of interest.
+  int dbg;
 };
 
 // KB = K elements per pipeline step: 32 (64 B rows, SWIZZLE_64B) for wide tiles, 64 (128 B rows, SWIZZLE_128B) for BN <= 128
@@ -161,6 +167,10 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + (tmem_slot - sbase));
+  // everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the tail of the previous kernel of the stream
+  // when this one was launched with programmatic stream serialisation; from here on its results are read
+  pdl_wait();
+  pdl_launch();
 
   // tile id -> (m tile, group, n tile); n fastest so that CTAs running together share the A tile / halo in L2
   auto decode = [&](int tile, int& mt, int& g, int& n0) {
@@ -181,7 +191,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
         if (b_resident && it > 0) break;     // resident weights: loaded with the first tile only (one group / N tile per launch)
         for (int kc = 0; kc < nk; ++kc, ++it) {
           const int s = it % NS;
-          mbar_wait(empty_b(s), ((it / NS) & 1) ^ 1);
+          if (p.dbg & 256) mbar_wait_spin(empty_b(s), ((it / NS) & 1) ^ 1); else mbar_wait(empty_b(s), ((it / NS) & 1) ^ 1);
+          if (MODE == MODE_GEMM && (p.dbg & 2) && it >= NS) { mbar_arrive(full_b(s)); continue; }
           mbar_expect_tx(full_b(s), Cfg::kStage);
           const uint32_t st = ring + s * Cfg::kStage;
           int kcol;
@@ -228,7 +239,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
     int it = 0, ita = 0, tl = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
       const int as = tl & 1;
-      mbar_wait(tmem_empty(as), ((tl >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator
+      if (p.dbg & 256) mbar_wait_spin(tmem_empty(as), ((tl >> 1) & 1) ^ 1); else mbar_wait(tmem_empty(as), ((tl >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t acc = tmem + (uint32_t)(as * BN);
       for (int kc = 0; kc < nk; ++kc, ++it) {
@@ -250,7 +261,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
           a_lo = a_hi + Cfg::kAPlane;
         }
         const int sb = b_resident ? kc : s;                                   // resident weights: step kc lives in slot kc
-        if (!b_resident || tl == 0) mbar_wait(full_b(sb), b_resident ? 0 : ((it / NS) & 1));
+        if (!b_resident || tl == 0) { if (p.dbg & 256) mbar_wait_spin(full_b(sb), b_resident ? 0 : ((it / NS) & 1)); else mbar_wait(full_b(sb), b_resident ? 0 : ((it / NS) & 1)); }
         tc_fence_after();
         if (lane == 0) {
           const uint32_t b_hi = ring + sb * Cfg::kStage + (MODE == MODE_GEMM ? 2 * Cfg::kAPlane : 0);
@@ -262,6 +273,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
           uint64_t dbl = dbh + (uint64_t)(Cfg::kBPlane >> 4);
 #pragma unroll
           for (int kk = 0; kk < KB / 16; ++kk) {
+            if (MODE == MODE_GEMM && (p.dbg & 4)) break;
             umma_bf16(acc, dal, dbh, Cfg::kIdesc, (kc | kk) ? 1u : 0u);
             umma_bf16(acc, dah, dbl, Cfg::kIdesc, 1u);
             umma_bf16(acc, dah, dbh, Cfg::kIdesc, 1u);
@@ -301,7 +313,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
         const int as = tl & 1;
         const int row0 = mt * 128 + q * 32;
         const int nch = ((p.N - n0 < BN ? p.N - n0 : BN) + 31) / 32;
-        for (int j = lane; j < BN; j += 32) {
+        for (int j = lane; j < BN && !(p.dbg & 64); j += 32) {
           const bool ok = n0 + j < p.N;
           bias_s[j] = (p.bias_mode && ok) ? __ldg(p.bias + n0 + j) : 0.f;
           gamma_s[j] = (p.gamma && ok) ? __ldg(p.gamma + n0 + j) : 1.f;
@@ -313,12 +325,18 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
           mbar_expect_tx(res_bar(ew, cc & 1), 4096);
           tma_load_2d(stg + (cc & 1) * 4096, &maps.res, res_bar(ew, cc & 1), p.r_coff + n0 + ch0 * 32, row0);
         }
-        mbar_wait(tmem_full(as), (tl >> 1) & 1);
+        if (p.dbg & 512) mbar_wait_spin(tmem_full(as), (tl >> 1) & 1); else mbar_wait(tmem_full(as), (tl >> 1) & 1);
         tc_fence_after();
 #pragma unroll 1
         for (int ch = ch0; ch < nch; ch += 2) {
+          if (p.dbg & 128) break;
           uint32_t v[32];
-          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + ch * 32), v);
+          if (p.dbg & 8) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = (uint32_t)(lane + j);
+          } else {
+            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + ch * 32), v);
+          }
           if (!warp_active) continue;                                  // whole warp beyond the matrix (warp-uniform)
           const int ob = cc & 1;
           if (lane == 0) {
@@ -328,7 +346,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
                 mbar_expect_tx(res_bar(ew, ob ^ 1), 4096);
                 tma_load_2d(stg + (ob ^ 1) * 4096, &maps.res, res_bar(ew, ob ^ 1), p.r_coff + n0 + (ch + 2) * 32, row0);
               }
-            } else {
+            } else if (!(p.dbg & 32)) {
               bulk_wait_read<1>();                                     // the store that used tile ob two chunks ago has read it
             }
           }
@@ -385,9 +403,9 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
               *reinterpret_cast<uint4*>(ob_p + 2048 + off) = l;
             }
           }
-          fence_proxy_async_smem();
+          if (!(p.dbg & 16)) fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (lane == 0 && !(p.dbg & 1)) {
             const int col = n0 + ch * 32;
             if (p.C) tma_store_2d(&maps.c, stg + ob * 4096, p.c_coff + col, row0);
             else { tma_store_2d(&maps.s_hi, stg + ob * 4096, p.s_coff + col, row0); tma_store_2d(&maps.s_lo, stg + ob * 4096 + 2048, p.s_coff + col, row0); }

@@ -81,7 +81,10 @@ inline cudaError_t stem_conv_launch(const float* in, int ldin, int B, int H, int
 template <int MAXQ, int LANES>   // float4 quads per lane; LANES (32 or 16) lanes cooperate on one row: lane owns quads lane + LANES*i
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ in, float* __restrict__ out, long long rows, int C,
                                                         const float* __restrict__ gw, const float* __restrict__ gb, float eps,
-                                                        __nv_bfloat16* __restrict__ shi, __nv_bfloat16* __restrict__ slo) {
+                                                        __nv_bfloat16* __restrict__ shi, __nv_bfloat16* __restrict__ slo,
+                                                        __nv_bfloat16* __restrict__ phi, __nv_bfloat16* __restrict__ plo, int R, int sr) {
+  pdl_wait();
+  pdl_launch();
   constexpr int RPW = 32 / LANES;       // rows per warp
   const int lane = threadIdx.x & (LANES - 1);
   const long long row = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + ((threadIdx.x & 31) / LANES);
@@ -111,6 +114,17 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   for (int o = LANES / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
   const float rstd = 1.0f / sqrtf(q / (float)C + eps);
   if (!ok) return;
+  // optional second copy in PATCH order for a k = s = sr convolution that follows (spatial-reduction conv of the attention,
+  // mix_transformers.py:112-117; ConvNeXt downsample 2x2/2, convnext.py:93-99): token (b, y, x) of an R x R map goes to row
+  // (b, y / sr, x / sr), columns ((y % sr) * sr + x % sr) * C + c -- the im2col matrix of that convolution, written by the
+  // producer instead of a separate gather kernel
+  long long prow = 0;
+  if (phi) {
+    const int x = (int)(row % R), y = (int)((row / R) % R);
+    const long long b = row / ((long long)R * R);
+    const int OR = R / sr;
+    prow = (((b * OR + y / sr) * OR + x / sr) * (sr * sr) + (y % sr) * sr + x % sr) * C;
+  }
 #pragma unroll
   for (int i = 0; i < MAXQ; ++i) {
     const int qd = lane + LANES * i;
@@ -120,18 +134,19 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                    (v[i].z - mean) * rstd * w.z + b.z, (v[i].w - mean) * rstd * w.w + b.w);
       if (out) reinterpret_cast<float4*>(out + row * C)[qd] = y;
       if (shi) store_split4(shi, slo, row * C + qd * 4, y);
+      if (phi) store_split4(phi, plo, prow + qd * 4, y);
     }
   }
 }
 
 inline cudaError_t layernorm_launch(const float* in, float* out, long long rows, int C, const float* w, const float* b, float eps,
-                                    cudaStream_t st, SplitT sp = SplitT()) {
+                                    cudaStream_t st, SplitT sp = SplitT(), SplitT patch = SplitT(), int R = 0, int sr = 0) {
   if (C % 4 || C > 768) return cudaErrorInvalidValue;
-  if (C <= 64) layernorm_kernel<1, 16><<<(unsigned)cdivl(rows, 16), 256, 0, st>>>(in, out, rows, C, w, b, eps, sp.hi, sp.lo);   // two rows per warp
-  else if (C <= 128) layernorm_kernel<1, 32><<<(unsigned)cdivl(rows, 8), 256, 0, st>>>(in, out, rows, C, w, b, eps, sp.hi, sp.lo);
-  else if (C <= 384) layernorm_kernel<3, 32><<<(unsigned)cdivl(rows, 8), 256, 0, st>>>(in, out, rows, C, w, b, eps, sp.hi, sp.lo);
-  else layernorm_kernel<6, 32><<<(unsigned)cdivl(rows, 8), 256, 0, st>>>(in, out, rows, C, w, b, eps, sp.hi, sp.lo);
-  return cudaGetLastError();
+  if (patch.hi && (R < 1 || sr < 1 || R % sr || rows % ((long long)R * R))) return cudaErrorInvalidValue;
+  if (C <= 64) return launch_pdl(layernorm_kernel<1, 16>, dim3((unsigned)cdivl(rows, 16)), dim3(256), 0, st, in, out, rows, C, w, b, eps, sp.hi, sp.lo, patch.hi, patch.lo, R, sr);   // two rows per warp
+  if (C <= 128) return launch_pdl(layernorm_kernel<1, 32>, dim3((unsigned)cdivl(rows, 8)), dim3(256), 0, st, in, out, rows, C, w, b, eps, sp.hi, sp.lo, patch.hi, patch.lo, R, sr);
+  if (C <= 384) return launch_pdl(layernorm_kernel<3, 32>, dim3((unsigned)cdivl(rows, 8)), dim3(256), 0, st, in, out, rows, C, w, b, eps, sp.hi, sp.lo, patch.hi, patch.lo, R, sr);
+  return launch_pdl(layernorm_kernel<6, 32>, dim3((unsigned)cdivl(rows, 8)), dim3(256), 0, st, in, out, rows, C, w, b, eps, sp.hi, sp.lo, patch.hi, patch.lo, R, sr);
 }
 
 // =====================================================================================================
@@ -222,6 +237,8 @@ inline cudaError_t attention_launch(const float* q, const float* kv, float* out,
 __global__ void __launch_bounds__(256) dwconv3x3_gelu_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C,
                                                              const float* __restrict__ w, const float* __restrict__ bias,
                                                              __nv_bfloat16* __restrict__ shi = nullptr, __nv_bfloat16* __restrict__ slo = nullptr) {
+  pdl_wait();
+  pdl_launch();
   // thread = 4 channels x (2 rows x 4 consecutive pixels): 24 activation + 9 weight loads (float4) for 8 outputs
   const int C4 = C >> 2, XG = (W + 3) >> 2, YG = (H + 1) >> 1;
   const unsigned total = (unsigned)B * YG * XG * C4;      // < 2^31 for every layer of the network: 32-bit index math
@@ -281,6 +298,8 @@ __global__ void __launch_bounds__(256) dwconv3x3_gelu_kernel(const float* __rest
 // 112 activation loads (16 B) for 3136 FMAs, which balances the L1 path against the FMA pipe (one row x 4 pixels was L1-bound 2.4x)
 __global__ void __launch_bounds__(256) dwconv7x7_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C,
                                                         const float* __restrict__ w, const float* __restrict__ bias) {
+  pdl_wait();
+  pdl_launch();
   const int C4 = C >> 2, XG = (W + 7) >> 3, YG = (H + 1) >> 1;
   const unsigned total = (unsigned)B * YG * XG * C4;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -332,6 +351,115 @@ __global__ void __launch_bounds__(256) dwconv7x7_kernel(const float* __restrict_
   }
 }
 
+// ConvNeXt block head fused: depthwise 7x7 + bias, then LayerNorm over the C channels of each pixel (eps 1e-6), written as the
+// bf16 hi/lo planes pwconv1 loads (convnext.py:48-50: dwconv -> permute -> norm).  The separate LayerNorm launch and the fp32
+// round trip of the depthwise output disappear.  Block = G pixel groups (2 rows x 8 pixels) x C/4 threads (4 channels each);
+// per pixel the C/4 partial sums meet in shared memory (two passes: mean, then centred variance -- as layernorm_kernel).
+template <int C>
+__global__ void __launch_bounds__(C / 4 * (C <= 192 ? 240 / (C / 4) : (C == 384 ? 2 : 1))) dwconv7x7_ln_kernel(
+    const float* __restrict__ in, int B, int H, int W, const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ gw,
+    const float* __restrict__ gb, float eps, __nv_bfloat16* __restrict__ shi, __nv_bfloat16* __restrict__ slo) {
+  constexpr int C4 = C / 4, G = C <= 192 ? 240 / C4 : (C == 384 ? 2 : 1);
+  __shared__ float s_sum[G][16], s_sq[G][16];
+  pdl_wait();
+  pdl_launch();
+  const int XG = (W + 7) >> 3, YG = (H + 1) >> 1;
+  const int ngroups = B * YG * XG;
+  const int g = threadIdx.x / C4, c4 = threadIdx.x - g * C4;
+  for (int base = blockIdx.x * G; base < ngroups; base += gridDim.x * G) {   // block-uniform trip count
+    const int grp = base + g;
+    const bool live = grp < ngroups;
+    if (threadIdx.x < G * 16) { s_sum[threadIdx.x / 16][threadIdx.x % 16] = 0.f; s_sq[threadIdx.x / 16][threadIdx.x % 16] = 0.f; }
+    __syncthreads();
+    int r = live ? grp : 0;
+    const int xg = r % XG; r /= XG;
+    const int y0 = (r % YG) * 2; const int b = r / YG;
+    const int x0 = xg * 8;
+    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias) + c4);
+    float4 acc[2][8];
+#pragma unroll
+    for (int oy = 0; oy < 2; ++oy)
+#pragma unroll
+      for (int p = 0; p < 8; ++p) acc[oy][p] = bv;
+    if (live) {
+#pragma unroll
+      for (int ry = 0; ry < 8; ++ry) {          // input rows y0-3 .. y0+4
+        const int iy = y0 + ry - 3;
+        if ((unsigned)iy >= (unsigned)H) continue;
+        float4 a[14];
+#pragma unroll
+        for (int j = 0; j < 14; ++j) {
+          const int ix = x0 - 3 + j;
+          a[j] = (unsigned)ix < (unsigned)W ? __ldg(reinterpret_cast<const float4*>(in + ((long long)(b * H + iy) * W + ix) * C) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int oy = 0; oy < 2; ++oy) {
+          const int ky = ry - oy;
+          if (ky < 0 || ky > 6) continue;
+#pragma unroll
+          for (int kx = 0; kx < 7; ++kx) {
+            const float4 k = __ldg(reinterpret_cast<const float4*>(w + (ky * 7 + kx) * C) + c4);
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+              acc[oy][p].x = fmaf(a[p + kx].x, k.x, acc[oy][p].x); acc[oy][p].y = fmaf(a[p + kx].y, k.y, acc[oy][p].y);
+              acc[oy][p].z = fmaf(a[p + kx].z, k.z, acc[oy][p].z); acc[oy][p].w = fmaf(a[p + kx].w, k.w, acc[oy][p].w);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int oy = 0; oy < 2; ++oy)
+#pragma unroll
+        for (int p = 0; p < 8; ++p) atomicAdd(&s_sum[g][oy * 8 + p], (acc[oy][p].x + acc[oy][p].y) + (acc[oy][p].z + acc[oy][p].w));
+    }
+    __syncthreads();
+    float mean[2][8];
+#pragma unroll
+    for (int oy = 0; oy < 2; ++oy)
+#pragma unroll
+      for (int p = 0; p < 8; ++p) mean[oy][p] = s_sum[g][oy * 8 + p] / (float)C;
+    if (live) {
+#pragma unroll
+      for (int oy = 0; oy < 2; ++oy)
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+          const float a0 = acc[oy][p].x - mean[oy][p], a1 = acc[oy][p].y - mean[oy][p], a2 = acc[oy][p].z - mean[oy][p], a3 = acc[oy][p].w - mean[oy][p];
+          atomicAdd(&s_sq[g][oy * 8 + p], fmaf(a0, a0, a1 * a1) + fmaf(a2, a2, a3 * a3));
+        }
+    }
+    __syncthreads();
+    if (live) {
+      const float4 lw = __ldg(reinterpret_cast<const float4*>(gw) + c4), lb = __ldg(reinterpret_cast<const float4*>(gb) + c4);
+#pragma unroll
+      for (int oy = 0; oy < 2; ++oy) {
+        if (y0 + oy >= H) break;
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+          if (x0 + p >= W) break;
+          const float rstd = 1.0f / sqrtf(s_sq[g][oy * 8 + p] / (float)C + eps), m = mean[oy][p];
+          const float4 y = make_float4((acc[oy][p].x - m) * rstd * lw.x + lb.x, (acc[oy][p].y - m) * rstd * lw.y + lb.y,
+                                       (acc[oy][p].z - m) * rstd * lw.z + lb.z, (acc[oy][p].w - m) * rstd * lw.w + lb.w);
+          store_split4(shi, slo, ((long long)(b * H + y0 + oy) * W + x0 + p) * C + c4 * 4, y);
+        }
+      }
+    }
+    __syncthreads();    // the sums are cleared at the top of the next trip
+  }
+}
+
+inline cudaError_t dwconv7x7_ln_launch(const float* in, int B, int H, int W, int C, const float* w, const float* bias, const float* gw, const float* gb,
+                                       float eps, SplitT out, cudaStream_t st) {
+  const int ngroups = B * ((H + 1) / 2) * ((W + 7) / 8);
+  auto grid = [&](int G) { const int g = cdiv(ngroups, G); return dim3((unsigned)(g < 148 * 8 ? g : 148 * 8)); };
+  switch (C) {
+    case 96: return launch_pdl(dwconv7x7_ln_kernel<96>, grid(10), dim3(240), 0, st, in, B, H, W, w, bias, gw, gb, eps, out.hi, out.lo);
+    case 192: return launch_pdl(dwconv7x7_ln_kernel<192>, grid(5), dim3(240), 0, st, in, B, H, W, w, bias, gw, gb, eps, out.hi, out.lo);
+    case 384: return launch_pdl(dwconv7x7_ln_kernel<384>, grid(2), dim3(192), 0, st, in, B, H, W, w, bias, gw, gb, eps, out.hi, out.lo);
+    case 768: return launch_pdl(dwconv7x7_ln_kernel<768>, grid(1), dim3(192), 0, st, in, B, H, W, w, bias, gw, gb, eps, out.hi, out.lo);
+  }
+  return cudaErrorInvalidValue;
+}
+
 inline unsigned ew_grid(long long total) {
   long long g = cdivl(total, 256);
   const long long cap = 148LL * 32;
@@ -344,6 +472,8 @@ inline unsigned ew_grid(long long total) {
 // `in` channel pitch/offset (ldi, icoff) select one head's half of a 512-channel tensor.
 __global__ void __launch_bounds__(256) upsample2x_kernel(const float* __restrict__ in, int ldi, int icoff, float* __restrict__ out, int ldo, int ocoff,
                                                          int B, int H, int W, int C, __nv_bfloat16* __restrict__ shi = nullptr, __nv_bfloat16* __restrict__ slo = nullptr) {
+  pdl_wait();
+  pdl_launch();
   // thread = 8 channels of one output pixel (16 B stores to each bf16 plane)
   const int C8 = C >> 3, OH = 2 * H, OW = 2 * W;
   const unsigned total = (unsigned)B * OH * OW * C8;     // <= 2^29 for the network's largest tensor at batch 32
@@ -391,6 +521,8 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) im2col_split_kernel(const __nv_bfloat16* __restrict__ shi, const __nv_bfloat16* __restrict__ slo, int lds,
                                                            __nv_bfloat16* __restrict__ dhi, __nv_bfloat16* __restrict__ dlo,
                                                            int B, int H, int W, int C, int OH, int OW, int KH, int stride, int pad) {
+  pdl_wait();
+  pdl_launch();
   const int C8 = C >> 3;
   const long long total = (long long)B * OH * OW * KH * KH * C8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -417,6 +549,8 @@ __global__ void __launch_bounds__(256) im2col_split_kernel(const __nv_bfloat16* 
 // stems run on the TMA GEMM engine too.  One thread = one output pixel x 8 consecutive K columns (16 B per plane).
 __global__ void __launch_bounds__(256) stem_gather_kernel(const float* __restrict__ x0, __nv_bfloat16* __restrict__ dhi, __nv_bfloat16* __restrict__ dlo,
                                                           int B, int OH, int OW, int stride) {
+  pdl_wait();
+  pdl_launch();
   constexpr int KP = 160, KQ = KP / 8;
   const unsigned total = (unsigned)B * OH * OW * KQ;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {

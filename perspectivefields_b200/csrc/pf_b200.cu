@@ -143,6 +143,9 @@ struct pf_engine {
   GemmW conv0, conv1;
   GemmW conv1p;                       // conv_fuse_conv1 composed with the x2 upsample in front of it: 4 phases x 32 outputs per head
   const float *conv1f_w, *conv1f_b;   // plain fp32 conv_fuse_conv1 [head][tap][ci][o] / bias, for the border-ring kernel
+  bool use_pair = true;               // option "pair": GEMM-mode launches with enough tiles run on CTA pairs (gemm2_tma.cuh, cta_group::2)
+  bool use_dwln = false;              // option "dw_ln": ConvNeXt depthwise 7x7 fused with the LayerNorm that follows it
+  bool use_pdl = true;                // option "pdl": programmatic dependent launch of the graph's kernels (common.cuh)
   bool decode_only = false;           // option "decode_only": classification heads return decoded fields, logits are never written
   bool use_attn_split = true;         // option "attn_split": q / kv leave their GEMMs as split planes (0 = fp32, split inside the attention kernel)
   bool use_phase = true;              // option "phase_conv1": 0 = materialise the upsampled tensor and run conv1 at 320x320
@@ -426,13 +429,17 @@ struct Fwd {
     TmaGemmParams p{};
     p.M = (int)M; p.Cin = K; p.N = N; p.K = K; p.a_c0 = a_c0; p.groups = 1;
     fill_epi(p, w, o, 0);
+    if (const char* d = getenv("PF_GEMM_DBG")) p.dbg = atoi(d);      // timing experiments only (gemm_tma.cuh: TmaGemmParams::dbg)
     TmaMaps maps{};
-    const int bn = tma_pick_bn(N, MODE_GEMM), kb = tma_pick_kb(bn, K, MODE_GEMM);
+    const int bn = tma_pick_bn(N, MODE_GEMM);
+    // CTA-pair kernel (256 x BN tiles, tcgen05.mma.cta_group::2: half the weight traffic per SM) when there are enough pair tiles
+    const int pair_clusters = (e->use_pair && !getenv("PF_NO_PAIR")) ? gemm2_plan(e->device, (int)M, N, bn) : 0;
+    const int kb = pair_clusters ? 32 : tma_pick_kb(bn, K, MODE_GEMM);
     const char* msg = nullptr;
     if (!msg) msg = map2d(&maps.a_hi, A.hi, A.ld, M, A.ld, 128, kb);
     if (!msg) msg = map2d(&maps.a_lo, A.lo, A.ld, M, A.ld, 128, kb);
-    if (!msg) msg = map2d(&maps.b_hi, w.hi, K, N, K, bn, kb);
-    if (!msg) msg = map2d(&maps.b_lo, w.lo, K, N, K, bn, kb);
+    if (!msg) msg = map2d(&maps.b_hi, w.hi, K, N, K, pair_clusters ? bn / 2 : bn, kb);
+    if (!msg) msg = map2d(&maps.b_lo, w.lo, K, N, K, pair_clusters ? bn / 2 : bn, kb);
     // epilogue tiles go through TMA as well: fp32 output, or (when there is no fp32 output) the split planes; residual
     if (o.C && o.S.hi) return fail(PF_ERR_ARG, "tgemm: fp32 and split outputs together are not supported in GEMM mode");
     if (o.res2 || o.bias_mode == 2) return fail(PF_ERR_ARG, "tgemm: second residual / border-class bias are halo-mode features");
@@ -445,7 +452,30 @@ struct Fwd {
     if (!o.C) maps.c = maps.a_hi;
     if (!o.S.hi) { maps.s_hi = maps.a_hi; maps.s_lo = maps.a_hi; }
     if (!o.res) maps.res = maps.a_hi;
+    if (pair_clusters) return launch_pair(maps, p, bn, pair_clusters);
     return launch_tma(MODE_GEMM, maps, p);
+  }
+  static cudaError_t gemm_tma_pair_mode(const TmaMaps& maps, const TmaGemmParams& p, int bn, int nclusters, cudaStream_t st) {
+    return gemm2_launch(maps, p, bn, nclusters, st);
+  }
+  int launch_pair(const TmaMaps& maps, const TmaGemmParams& p, int bn, int nclusters) {
+    if (e->profile) {
+      pf_engine::ProfRec r{};
+      for (cudaEvent_t* ev : {&r.a, &r.b}) {
+        if (e->ev_pool.empty()) { CU(cudaEventCreate(ev)); }
+        else { *ev = e->ev_pool.back(); e->ev_pool.pop_back(); }
+      }
+      r.flops = 2.0 * (double)p.M * (double)p.N * (double)p.K;
+      r.cfg = 5;
+      r.M = p.M; r.N = p.N; r.K = p.K; r.KH = 1; r.stride = 2; r.groups = 1; r.Cin = p.Cin;   // (stride 2 marks pair launches in the CSV)
+      CU(cudaEventRecord(r.a, st));
+      LAUNCHED(gemm_tma_pair_mode(maps, p, bn, nclusters, st));
+      CU(cudaEventRecord(r.b, st));
+      e->prof.push_back(r);
+      return PF_OK;
+    }
+    LAUNCHED(gemm_tma_pair_mode(maps, p, bn, nclusters, st));
+    return PF_OK;
   }
   // 3x3 / stride 1 / pad 1 convolution on split NHWC planes (optionally a second source for channels >= c_split)
   int thalo(const SplitT& A, int a_c0, int a_gc, const SplitT* A2, int c_split, int a2_c0, int B, int H, int W, int Cin, const GemmW& w, int N,
@@ -465,9 +495,9 @@ struct Fwd {
       if (!msg) msg = map_halo(&maps.a2_hi, A2->hi, B, H, W, A2->ld);
       if (!msg) msg = map_halo(&maps.a2_lo, A2->lo, B, H, W, A2->ld);
     } else { maps.a2_hi = maps.a_hi; maps.a2_lo = maps.a_lo; }
-    maps.c = maps.a_hi; maps.s_hi = maps.a_hi; maps.s_lo = maps.a_hi; maps.res = maps.a_hi;   // halo mode: epilogue stores from registers
     if (!msg) msg = map2d(&maps.b_hi, w.hi, p.K, (long long)groups * N, p.K, bn, kb);
     if (!msg) msg = map2d(&maps.b_lo, w.lo, p.K, (long long)groups * N, p.K, bn, kb);
+    maps.c = maps.a_hi; maps.s_hi = maps.a_hi; maps.s_lo = maps.a_hi; maps.res = maps.a_hi;   // halo mode: epilogue stores from registers
     if (msg) return fail(PF_ERR_CUDA, "%s", msg);
     return launch_tma(MODE_HALO, maps, p, pred);
   }
@@ -480,7 +510,7 @@ struct Fwd {
     SplitT col = salloc(M, K);
     if (!dry) {
       if (Cin % 8) return fail(PF_ERR_ARG, "tconv_gather: Cin %% 8");
-      LAUNCHED((im2col_split_kernel<<<ew_grid(M * K / 8), 256, 0, st>>>(A.hi, A.lo, A.ld, col.hi, col.lo, B, H, W, Cin, OH, OW, KH, stride, pad), cudaGetLastError()));
+      LAUNCHED(launch_pdl(im2col_split_kernel, dim3(ew_grid(M * K / 8)), dim3(256), 0, st, A.hi, A.lo, A.ld, col.hi, col.lo, B, H, W, Cin, OH, OW, KH, stride, pad));
     }
     int r = tgemm(col, M, K, 0, w, N, o);
     ar.release(m);
@@ -489,6 +519,12 @@ struct Fwd {
   int ln_split(const float* x, const SplitT& y, long long rows, int C, const LnW& w, float eps, float* yf = nullptr) {
     if (dry) return PF_OK;
     LAUNCHED(layernorm_launch(x, yf, rows, C, w.w, w.b, eps, st, y));
+    return PF_OK;
+  }
+  // LayerNorm whose output is (also) written in patch order for a k = s = sr convolution on the R x R map (y may be empty)
+  int ln_split_patch(const float* x, const SplitT& y, const SplitT& patch, long long rows, int C, const LnW& w, float eps, int R, int sr) {
+    if (dry) return PF_OK;
+    LAUNCHED(layernorm_launch(x, nullptr, rows, C, w.w, w.b, eps, st, y, patch, R, sr));
     return PF_OK;
   }
   int ln(const float* x, float* y, long long rows, int C, const LnW& w, float eps) {
@@ -592,10 +628,10 @@ static int launch_postprocess(const float* vec, const float* lat, int n, const i
     total += (long long)height[i] * width[i];
     if (height[i] > max_h) max_h = height[i];
     const int wp = (width[i] + 3) / 4 * 4;
-    if (wp > max_wp) max_wp = wp;
+    if (wp <= kPostMaxW && wp > max_wp) max_wp = wp;    // (wider images take the table-less path of the kernel)
   }
   CU(cudaMemcpyAsync(d_post, post.data(), n * sizeof(PostImage), cudaMemcpyHostToDevice, st));
-  const int smem = (max_wp <= kPostMaxW ? max_wp : 4) * 8;
+  const int smem = max_wp * 8;
   LAUNCHED((postprocess_kernel<<<dim3((unsigned)cdiv(max_h, kPostBand), (unsigned)n), kPostThreads, smem, st>>>(vec, lat, d_post, g_out, l_out, lat_is_sin),
             cudaGetLastError()));
   return PF_OK;
@@ -693,7 +729,7 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
     const long long m = ar.mark();
     const long long M = (long long)n * 160 * 160;
     SplitT col = F.salloc(M, 160);
-    if (!dry) LAUNCHED((stem_gather_kernel<<<ew_grid(M * 20), 256, 0, st>>>(x0, col.hi, col.lo, n, 160, 160, 2), cudaGetLastError()));
+    if (!dry) LAUNCHED(launch_pdl(stem_gather_kernel, dim3(ew_grid(M * 20)), dim3(256), 0, st, x0, col.hi, col.lo, n, 160, 160, 2));
     Epi o; o.S = ll; o.act = 1;
     TRY(F.tgemm(col, M, 160, 0, e->llencg, 64, o));
     ar.release(m);
@@ -711,6 +747,8 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
     float* x = ar.f(rows * C);
     float* tf = ar.f(rows * C);                      // patch-embed conv output (before its LayerNorm)
     SplitT t1 = F.salloc(rows, C);                   // LayerNorm output (GEMM input only)
+    SplitT t1p;                                      // the same in patch order [n*100, sr*sr*C]: A operand of the spatial-reduction conv
+    if (sr > 1) t1p = F.salloc((long long)n * 100, sr * sr * C);
     SplitT q = F.salloc(rows, C);                    // q and kv leave their GEMMs as split planes: the attention core's MMA operands
     SplitT a = F.salloc(rows, C);                    // attention output
     float* t2f = ar.f((long long)n * 100 * C);
@@ -724,7 +762,7 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
     if (s == 0 && e->use_stem_tc) {
       const long long mm = ar.mark();
       SplitT col = F.salloc(rows, 160);
-      if (!dry) LAUNCHED((stem_gather_kernel<<<ew_grid(rows * 20), 256, 0, st>>>(x0, col.hi, col.lo, n, 80, 80, 4), cudaGetLastError()));
+      if (!dry) LAUNCHED(launch_pdl(stem_gather_kernel, dim3(ew_grid(rows * 20)), dim3(256), 0, st, x0, col.hi, col.lo, n, 80, 80, 4));
       Epi o; o.C = tf; o.ldc = C;
       TRY(F.tgemm(col, rows, 160, 0, e->embed1g, 64, o));
       ar.release(mm);
@@ -738,12 +776,13 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
     TRY(F.tapf(x, rows * C, "mit.s%d.embed", s + 1));
     for (int i = 0; i < kMitDepths[s]; ++i) {
       const MitBlockW& b = e->blocks[s][i];
-      TRY(F.ln_split(x, t1, rows, C, b.ln1, 1e-6f));
+      if (sr > 1) TRY(F.ln_split_patch(x, t1, t1p, rows, C, b.ln1, 1e-6f, R, sr));     // + the sr conv's im2col matrix
+      else TRY(F.ln_split(x, t1, rows, C, b.ln1, 1e-6f));
       Epi oq, okv;
       if (qkv_split) { oq.S = q; okv.S = kv; } else { oq.C = qf; oq.ldc = C; okv.C = kvf; okv.ldc = 2 * C; }
       TRY(F.tgemm(t1, rows, C, 0, b.q, C, oq));
       if (sr > 1) {
-        { Epi o; o.C = t2f; o.ldc = C; TRY(F.tconv_gather(t1, n, R, R, C, sr, sr, 0, b.sr, C, o)); }
+        { Epi o; o.C = t2f; o.ldc = C; TRY(F.tgemm(t1p, (long long)n * 100, sr * sr * C, 0, b.sr, C, o)); }
         TRY(F.ln_split(t2f, t2, (long long)n * 100, C, b.srln, 1e-5f));
         TRY(F.tgemm(t2, (long long)n * 100, C, 0, b.kv, 2 * C, okv));
       } else {
@@ -758,7 +797,7 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
       TRY(F.tapf(x, rows * C, "mit.s%d.b%d.attn", s + 1, i));
       TRY(F.ln_split(x, t1, rows, C, b.ln2, 1e-6f));
       { Epi o; o.C = h1; o.ldc = 4 * C; TRY(F.tgemm(t1, rows, C, 0, b.fc1, 4 * C, o)); }
-      if (!dry) LAUNCHED((dwconv3x3_gelu_kernel<<<ew_grid((long long)n * ((R + 1) / 2) * ((R + 3) / 4) * C), 256, 0, st>>>(h1, nullptr, n, R, R, 4 * C, b.dw_w, b.dw_b, h2.hi, h2.lo), cudaGetLastError()));
+      if (!dry) LAUNCHED(launch_pdl(dwconv3x3_gelu_kernel, dim3(ew_grid((long long)n * ((R + 1) / 2) * ((R + 3) / 4) * C)), dim3(256), 0, st, h1, nullptr, n, R, R, 4 * C, b.dw_w, b.dw_b, h2.hi, h2.lo));
       { Epi o; o.C = x; o.ldc = C; o.res = x; o.ldr = C; TRY(F.tgemm(h2, rows, 4 * C, 0, b.fc2, C, o)); }
       TRY(F.tapf(x, rows * C, "mit.s%d.b%d", s + 1, i));
     }
@@ -805,12 +844,12 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
       { Epi o; o.C = w2; o.ldc = 512; o.res = of; o.ldr = 512; o.res_relu = 1; TRY(rcu(u, e->rcu[lvl - 1][1][1], o)); }
       if (lvl > 1) {
         float* up = ar.f(px * 4 * 512);
-        if (!dry) LAUNCHED((upsample2x_kernel<<<ew_grid(px * 4 * 64), 256, 0, st>>>(w2, 512, 0, up, 512, 0, n, r, r, 512), cudaGetLastError()));
+        if (!dry) LAUNCHED(launch_pdl(upsample2x_kernel, dim3(ew_grid(px * 4 * 64)), dim3(256), 0, st, w2, 512, 0, up, 512, 0, n, r, r, 512, nullptr, nullptr));
         fused = up;
         TRY(F.tapf(up, px * 4 * 512, "head.fusion%d", lvl));
       } else {
         fused_s = F.salloc(px * 4, 512);
-        if (!dry) LAUNCHED((upsample2x_kernel<<<ew_grid(px * 4 * 64), 256, 0, st>>>(w2, 512, 0, nullptr, 512, 0, n, r, r, 512, fused_s.hi, fused_s.lo), cudaGetLastError()));
+        if (!dry) LAUNCHED(launch_pdl(upsample2x_kernel, dim3(ew_grid(px * 4 * 64)), dim3(256), 0, st, w2, 512, 0, nullptr, 512, 0, n, r, r, 512, fused_s.hi, fused_s.lo));
         TRY(F.tap_split("head.fusion1", fused_s, px * 4 * 512));
       }
     }
@@ -847,7 +886,7 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
         TRY(F.tap("head.conv0", c0, (long long)n * 160 * 160 * 128));
       }
       SplitT c0u = F.salloc((long long)n * kNet * kNet, 128);
-      if (!dry) LAUNCHED((upsample2x_kernel<<<ew_grid((long long)n * kNet * kNet * 16), 256, 0, st>>>(c0, 128, 0, nullptr, 128, 0, n, 160, 160, 128, c0u.hi, c0u.lo), cudaGetLastError()));
+      if (!dry) LAUNCHED(launch_pdl(upsample2x_kernel, dim3(ew_grid((long long)n * kNet * kNet * 16)), dim3(256), 0, st, c0, 128, 0, nullptr, 128, 0, n, 160, 160, 128, c0u.hi, c0u.lo));
       Epi o; o.ldc = 64; o.c_gcoff = 32; o.act = 1;
       if (keep_conv1) o.C = conv1_out;
       TRY(F.thalo(c0u, 0, 64, nullptr, 0, 0, n, kNet, kNet, 64, e->conv1, 32, 2, 32, o, fuse_pred ? pt : nullptr));
@@ -873,11 +912,11 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
       const int C = kCnxDims[s];
       if (s > 0) {
         const int r2 = r / 2;
-        SplitT y = F.salloc((long long)n * r * r, kCnxDims[s - 1]);
-        TRY(F.ln_split(x, y, (long long)n * r * r, kCnxDims[s - 1], e->pn_ds_ln[s], 1e-6f));
+        SplitT y = F.salloc((long long)n * r2 * r2, 4 * kCnxDims[s - 1]);      // LayerNorm output written directly as the 2x2/2 conv's im2col matrix
+        TRY(F.ln_split_patch(x, SplitT(), y, (long long)n * r * r, kCnxDims[s - 1], e->pn_ds_ln[s], 1e-6f, r, 2));
         float* xn = ar.f((long long)n * r2 * r2 * C);
         Epi o; o.C = xn; o.ldc = C;
-        TRY(F.tconv_gather(y, n, r, r, kCnxDims[s - 1], 2, 2, 0, e->pn_ds[s], C, o));
+        TRY(F.tgemm(y, (long long)n * r2 * r2, 4 * kCnxDims[s - 1], 0, e->pn_ds[s], C, o));
         x = xn; r = r2;
       }
       const long long rows = (long long)n * r * r;
@@ -886,8 +925,12 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
       SplitT h = F.salloc(rows, 4 * C);
       for (int j = 0; j < kCnxDepths[s]; ++j) {
         const CnxBlockW& b = e->pn_blocks[s][j];
-        if (!dry) LAUNCHED((dwconv7x7_kernel<<<ew_grid((long long)n * ((r + 1) / 2) * ((r + 7) / 8) * (C / 4)), 256, 0, st>>>(x, yf, n, r, r, C, b.dw_w, b.dw_b), cudaGetLastError()));
-        TRY(F.ln_split(yf, y, rows, C, b.ln, 1e-6f));
+        if (e->use_dwln) {   // depthwise 7x7 + LayerNorm in one kernel, straight to the split planes pwconv1 loads
+          if (!dry) LAUNCHED(dwconv7x7_ln_launch(x, n, r, r, C, b.dw_w, b.dw_b, b.ln.w, b.ln.b, 1e-6f, y, st));
+        } else {
+          if (!dry) LAUNCHED(launch_pdl(dwconv7x7_kernel, dim3(ew_grid((long long)n * ((r + 1) / 2) * ((r + 7) / 8) * (C / 4))), dim3(256), 0, st, x, yf, n, r, r, C, b.dw_w, b.dw_b));
+          TRY(F.ln_split(yf, y, rows, C, b.ln, 1e-6f));
+        }
         { Epi o; o.S = h; o.act = 2; TRY(F.tgemm(y, rows, C, 0, b.pw1, 4 * C, o)); }
         { Epi o; o.C = x; o.ldc = C; o.res = x; o.ldr = C; o.gamma = b.gamma; TRY(F.tgemm(h, rows, 4 * C, 0, b.pw2, C, o)); }
       }
@@ -916,6 +959,11 @@ static int configure_device(int device) {
   std::lock_guard<std::mutex> lock(mu);
   if (device < (int)done.size() && done[device]) return PF_OK;
   CU(gemm_tma_configure_device());
+  {
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    CU(gemm2_configure_device(device, prop.multiProcessorCount));
+  }
   CU(attention_mma_configure_device());
   CU(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
   CU(cudaFuncSetAttribute(conv1_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingSmem));
@@ -1021,7 +1069,9 @@ int pf_forward(pf_handle h, const pf_batch* bt, void* workspace, int64_t workspa
   h->taps.clear();
   h->kp.st = (cudaStream_t)stream;
   tl_kp = &h->kp;
+  pdl_enabled() = h->use_pdl && !h->kp.on && !h->profile && !sync_debug();   // (event records between launches defeat it anyway)
   const int r = run_forward_tma(F, bt);
+  pdl_enabled() = false;
   tl_kp = nullptr;
   return r;
 }
@@ -1091,6 +1141,9 @@ int pf_set_option(pf_handle h, const char* name, int value) {
   if (!strcmp(name, "phase_conv1")) { h->use_phase = value != 0; return PF_OK; }
   if (!strcmp(name, "attn_split")) { h->use_attn_split = value != 0; return PF_OK; }
   if (!strcmp(name, "decode_only")) { h->decode_only = value != 0; return PF_OK; }
+  if (!strcmp(name, "pdl")) { h->use_pdl = value != 0; return PF_OK; }
+  if (!strcmp(name, "dw_ln")) { h->use_dwln = value != 0; return PF_OK; }
+  if (!strcmp(name, "pair")) { h->use_pair = value != 0; return PF_OK; }
   return fail(PF_ERR_ARG, "pf_set_option: unknown option '%s'", name);
 }
 // out[cfg*3 + {0,1,2}] = {milliseconds, algorithmic FLOPs, launches} per GEMM engine configuration (7 configs),
@@ -1410,6 +1463,11 @@ int pf_op_postprocess(const float* vec, const float* lat, int n, const int32_t* 
   return r;
 }
 
+int pf_op_fill_stream(float* dst, int64_t numel, float value, void* stream) {
+  if (!dst || numel < 4 || (numel & 3) || ((uintptr_t)dst & 15)) return fail(PF_ERR_ARG, "pf_op_fill_stream: bad argument");
+  LAUNCHED((fill_stream_kernel<<<148 * 16, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4*>(dst), numel / 4, value), cudaGetLastError()));
+  return PF_OK;
+}
 int pf_op_layernorm(const float* x, float* y, int64_t rows, int C, const float* w, const float* b, float eps, void* stream) {
   LAUNCHED(layernorm_launch(x, y, rows, C, w, b, eps, (cudaStream_t)stream));
   return PF_OK;
@@ -1428,17 +1486,17 @@ int pf_op_attention_mma(const float* q, const float* kv, float* out, int B, int 
 }
 int pf_op_dwconv3x3_gelu(const float* x, float* y, int B, int H, int W, int C, const float* w, const float* bias, void* stream) {
   if (C % 4) return fail(PF_ERR_ARG, "C %% 4");
-  LAUNCHED((dwconv3x3_gelu_kernel<<<ew_grid((long long)B * ((H + 1) / 2) * ((W + 3) / 4) * (C / 4)), 256, 0, (cudaStream_t)stream>>>(x, y, B, H, W, C, w, bias), cudaGetLastError()));
+  LAUNCHED(launch_pdl(dwconv3x3_gelu_kernel, dim3(ew_grid((long long)B * ((H + 1) / 2) * ((W + 3) / 4) * (C / 4))), dim3(256), 0, (cudaStream_t)stream, x, y, B, H, W, C, w, bias, nullptr, nullptr));
   return PF_OK;
 }
 int pf_op_dwconv7x7(const float* x, float* y, int B, int H, int W, int C, const float* w, const float* bias, void* stream) {
   if (C % 4) return fail(PF_ERR_ARG, "C %% 4");
-  LAUNCHED((dwconv7x7_kernel<<<ew_grid((long long)B * ((H + 1) / 2) * ((W + 7) / 8) * (C / 4)), 256, 0, (cudaStream_t)stream>>>(x, y, B, H, W, C, w, bias), cudaGetLastError()));
+  LAUNCHED(launch_pdl(dwconv7x7_kernel, dim3(ew_grid((long long)B * ((H + 1) / 2) * ((W + 7) / 8) * (C / 4))), dim3(256), 0, (cudaStream_t)stream, x, y, B, H, W, C, w, bias));
   return PF_OK;
 }
 int pf_op_upsample2x(const float* x, float* y, int B, int H, int W, int C, void* stream) {
   if (C % 8) return fail(PF_ERR_ARG, "C %% 8");
-  LAUNCHED((upsample2x_kernel<<<ew_grid((long long)B * H * W * C / 2), 256, 0, (cudaStream_t)stream>>>(x, C, 0, y, C, 0, B, H, W, C), cudaGetLastError()));
+  LAUNCHED(launch_pdl(upsample2x_kernel, dim3(ew_grid((long long)B * H * W * C / 2)), dim3(256), 0, (cudaStream_t)stream, x, C, 0, y, C, 0, B, H, W, C, nullptr, nullptr));
   return PF_OK;
 }
 int pf_op_preprocess(const uint8_t* img, int H, int W, const float* mean3, const float* std3, float* y, void* stream) {

@@ -160,7 +160,7 @@ __device__ __forceinline__ float fast_asinf(float x) {
   const float a = fabsf(x);
   const bool big = a > 0.5f;
   const float z = big ? (1.0f - a) * 0.5f : a * a;
-  const float s = big ? sqrtf(z) : a;
+  const float s = big ? z * rsqrtf(fmaxf(z, 1e-30f)) : a;       // sqrt z (z = 0 at |x| = 1 stays 0); rsqrt.approx: 2^-22 relative
   float p = 4.2163199048e-2f;
   p = fmaf(p, z, 2.4181311049e-2f);
   p = fmaf(p, z, 4.5470025998e-2f);
@@ -172,17 +172,18 @@ __device__ __forceinline__ float fast_asinf(float x) {
 }
 
 // Block = (band of kPostBand output rows, image).  Per group of kPostRows output rows the block first interpolates VERTICALLY:
-// for each of the 320 source columns and the three source planes (gravity x * W/320, gravity y * H/320, latitude) it stores
-// hy * src[y0][x] + ly * src[y1][x] in shared memory; then every thread produces 4 consecutive output pixels of one row from
-// two shared-memory taps per plane (per-column index / weight tables, built once per block), normalises the up-vector, applies
-// asin + rad2deg and writes three 16-byte streaming stores.  12 global loads per pixel become 6 shared loads, and the per-pixel
-// index arithmetic disappears: the kernel is bound by its 12 B/pixel of stores (bench.py roofline_post).
+// for each of the 320 source columns it stores (gravity x * W/320, gravity y * H/320, latitude) blended between the two source
+// rows as ONE float4 in shared memory; then every thread produces 4 consecutive output pixels of one row from two 16-byte
+// shared-memory taps per pixel (per-column index / weight tables, built once per block), normalises the up-vector
+// (v * rsqrt(max(|v|^2, 1e-24)) == v / max(|v|, 1e-12)), applies asin + rad2deg and writes three 16-byte streaming stores.
+// Measured before this version (ncu, profiles/r02_notes.md): 160 instructions per pixel, issue slots 70 % busy, DRAM 15 %:
+// instruction-bound; this version needs ~45 and is bound by its 12 B/pixel of stores.
 // The interpolation is evaluated as hx * (hy v00 + ly v10) + lx * (hy v01 + ly v11): ATen's bilinear kernel nests the two axes the
 // other way round (same weights, same products; the results differ by fp32 rounding only, ~1e-7 relative).
-constexpr int kPostRows = 4, kPostBand = 16, kPostThreads = 256, kPostMaxW = 4096;
+constexpr int kPostRows = 4, kPostBand = 16, kPostThreads = 256, kPostMaxW = 3072;   // (static 20.6 KB + 8 B per column <= 48 KB)
 __global__ void __launch_bounds__(kPostThreads) postprocess_kernel(const float* __restrict__ vec, const float* __restrict__ lat, const PostImage* __restrict__ imgs,
                                                                    float* __restrict__ g_out, float* __restrict__ l_out, int lat_is_sin) {
-  __shared__ float s_v[kPostRows][3][kNet + 1];      // vertically interpolated source rows (+1: tap xa + 1 of the last column)
+  __shared__ float4 s_v[kPostRows][kNet + 1];        // vertically interpolated source rows (+1: tap xa + 1 of the last column)
   extern __shared__ __align__(16) unsigned char s_dyn[];   // per output column: int xa, float lx  (W entries each, W padded to 4)
   const PostImage im = imgs[blockIdx.y];
   const int band0 = blockIdx.x * kPostBand;
@@ -208,6 +209,8 @@ __global__ void __launch_bounds__(kPostThreads) postprocess_kernel(const float* 
   const long long HW = (long long)im.H * im.W;
   const bool vec_ok = (im.W & 3) == 0 && (im.g_off & 3) == 0 && ((im.g_off + HW) & 3) == 0 && (im.l_off & 3) == 0;
   const int band1 = min(band0 + kPostBand, im.H);
+  // work items of one row group: (row rr, column group g), rr-major; thread `tid` starts at item tid and advances by 256
+  const int g_start = tid % W4, r_start = tid / W4, g_step = kPostThreads % W4, r_step = kPostThreads / W4;
   for (int r0 = band0; r0 < band1; r0 += kPostRows) {
     __syncthreads();     // (the previous group's readers are done; the column tables are complete)
     for (int i = tid; i < kPostRows * kNet; i += kPostThreads) {
@@ -218,15 +221,15 @@ __global__ void __launch_bounds__(kPostThreads) postprocess_kernel(const float* 
       const int y1 = y0 + (y0 < kNet - 1);
       const float ly = sy - (float)y0, hy = 1.f - ly;
       const int i0 = y0 * kNet + x, i1 = y1 * kNet + x;
-      s_v[rr][0][x] = hy * (__ldg(v0 + i0) * fx) + ly * (__ldg(v0 + i1) * fx);
-      s_v[rr][1][x] = hy * (__ldg(v1 + i0) * fy) + ly * (__ldg(v1 + i1) * fy);
-      s_v[rr][2][x] = hy * __ldg(lp + i0) + ly * __ldg(lp + i1);
-      if (x == kNet - 1) { s_v[rr][0][kNet] = s_v[rr][0][x]; s_v[rr][1][kNet] = s_v[rr][1][x]; s_v[rr][2][kNet] = s_v[rr][2][x]; }
+      const float4 t = make_float4(hy * (__ldg(v0 + i0) * fx) + ly * (__ldg(v0 + i1) * fx), hy * (__ldg(v1 + i0) * fy) + ly * (__ldg(v1 + i1) * fy),
+                                   hy * __ldg(lp + i0) + ly * __ldg(lp + i1), 0.f);
+      s_v[rr][x] = t;
+      if (x == kNet - 1) s_v[rr][kNet] = t;      // tap xa + 1 of column 319 (its weight lx is 0 there)
     }
     __syncthreads();
     const int rows = min(kPostRows, band1 - r0);
-    for (int it = tid; it < rows * W4; it += kPostThreads) {
-      const int rr = it / W4, x0 = (it - rr * W4) * 4;
+    for (int rr = r_start, g = g_start; rr < rows;) {
+      const int x0 = g * 4;
       int xa[4];
       float lx[4];
       if (tab) {
@@ -245,12 +248,12 @@ __global__ void __launch_bounds__(kPostThreads) postprocess_kernel(const float* 
       float ogx[4], ogy[4], ol[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        // tap xa + 1 is clamped to column 319 through the duplicated entry s_v[..][320] (its weight lx is 0 there anyway)
+        const float4 a = s_v[rr][xa[j]], b = s_v[rr][xa[j] + 1];
         const float hx = 1.f - lx[j];
-        const float gx = hx * s_v[rr][0][xa[j]] + lx[j] * s_v[rr][0][xa[j] + 1];
-        const float gy = hx * s_v[rr][1][xa[j]] + lx[j] * s_v[rr][1][xa[j] + 1];
-        float lv = hx * s_v[rr][2][xa[j]] + lx[j] * s_v[rr][2][xa[j] + 1];
-        const float inv = 1.0f / fmaxf(sqrtf(gx * gx + gy * gy), 1e-12f);     // F.normalize: v / max(|v|, eps)
+        const float gx = hx * a.x + lx[j] * b.x;
+        const float gy = hx * a.y + lx[j] * b.y;
+        float lv = hx * a.z + lx[j] * b.z;
+        const float inv = rsqrtf(fmaxf(fmaf(gx, gx, gy * gy), 1e-24f));     // F.normalize: v / max(|v|, 1e-12)
         ogx[j] = gx * inv; ogy[j] = gy * inv;
         if (lat_is_sin) lv = fast_asinf(lv) * (180.0f / 3.14159265358979323846f);
         ol[j] = lv;
@@ -265,6 +268,8 @@ __global__ void __launch_bounds__(kPostThreads) postprocess_kernel(const float* 
       } else {
         for (int j = 0; j < 4 && x0 + j < im.W; ++j) { gp[j] = ogx[j]; gp[HW + j] = ogy[j]; lpo[j] = ol[j]; }
       }
+      g += g_step; rr += r_step;
+      if (g >= W4) { g -= W4; ++rr; }
     }
   }
 }
@@ -288,8 +293,8 @@ constexpr int kCamChunk = 24;   // images per launch (the descriptors travel as 
 struct CamBatch { CamImage im[kCamChunk]; };
 
 // atan2(y, h) in DEGREES for h >= 0 (Cephes-style atanf: three ranges, odd polynomial on |r| <= tan(pi/8)); the range offset is
-// added in float64 so that the result is rounded to float32 once.  Max error 7.2e-6 degrees incl. that final rounding
-// (ulp(90)/2 = 3.8e-6), checked against float64 atan2 in tests/test_host_logic.py.
+// added by the same fma that converts to degrees, so the result is rounded once.  Max error 7.2e-6 degrees incl. that final
+// rounding (ulp(90)/2 = 3.8e-6), checked against float64 atan2 in tests/test_host_logic.py.
 __device__ __forceinline__ float fast_atan2_deg(float y, float h) {
   const float a = fabsf(y);
   const bool hi = a > 2.414213562373095f * h, mid = !hi && a > 0.4142135623730950f * h;
@@ -301,15 +306,17 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float h) {
   p = fmaf(p, z, 1.99777106478e-1f);
   p = fmaf(p, z, -3.33329491539e-1f);
   const float pr = fmaf(r * z, p, r);
-  const double off = hi ? 90.0 : (mid ? 45.0 : 0.0);
-  const float deg = (float)fma((double)pr, 57.29577951308232, off);
+  const float off = hi ? 90.0f : (mid ? 45.0f : 0.0f);              // exact in float32
+  const float deg = fmaf(pr, 57.29577951308232f, off);             // one rounding (the constant's own error: 1e-8 relative)
   return copysignf(deg, y);
 }
 
 // One thread = 4 consecutive pixels of one row.  The pixel -> ray map is linear: its three world components are evaluated in
-// float64 (x_j = linspace sample, one DFMA per component: 1e-16 relative, like the numpy reference), then rounded to float32 for
-// the square root, the division and the arctangent (fast_atan2_deg) -- the float64 sqrt / divide / atan2 per pixel of the first
-// version kept this kernel at 0.11 of the HBM roofline; it is now bound by its 12 B/pixel of stores.
+// float64 for the thread's FIRST pixel (x_j = linspace sample: 1e-16 relative, like the numpy reference), rounded to float32
+// and advanced by float32 steps for the other three (the steps are ~1/f: their rounding is 1e-10 absolute); square root,
+// division and arctangent are float32 (fast_atan2_deg).  History (ncu, profiles/r02_notes.md): float64 sqrt / divide / atan2 per
+// pixel: 0.11 of the HBM roofline; float64 linear forms + float32 transcendentals: 0.35, the XU pipe (conversions, MUFU) 68 %
+// busy with ~10 conversions / special-function operations per pixel; this version issues ~4.5.
 __global__ void __launch_bounds__(256) camera_fields_kernel(const __grid_constant__ CamBatch batch, float* __restrict__ up, float* __restrict__ lat) {
   const CamImage& c = batch.im[blockIdx.y];
   const int W4 = (c.W + 3) >> 2;
@@ -326,9 +333,10 @@ __global__ void __launch_bounds__(256) camera_fields_kernel(const __grid_constan
     } else {
       const double vvp_x = (c.sr * c.ce * c.f) / -c.se + c.cx, vvp_y = (c.cr * c.ce * c.f) / -c.se + c.cy;
       const float vy = (float)((vvp_y - ((double)i + 0.5)) * c.sgn);
+      const float vx0 = (float)((vvp_x - ((double)j0 + 0.5)) * c.sgn), dvx = (float)(-c.sgn);    // pixel k: vx0 + k * dvx
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float vx = (float)((vvp_x - ((double)(j0 + k) + 0.5)) * c.sgn);
+        const float vx = fmaf((float)k, dvx, vx0);
         const float inv = rsqrtf(fmaf(vx, vx, vy * vy));
         o[2 * k] = vx * inv; o[2 * k + 1] = vy * inv;
       }
@@ -352,13 +360,25 @@ __global__ void __launch_bounds__(256) camera_fields_kernel(const __grid_constan
     const double bx = -y * c.sr, by = y * c.ce * c.cr - c.se, bz = y * c.se * c.cr + c.ce;
     const double ax = c.cr, ay = c.ce * c.sr, az = c.se * c.sr;
     float o[4];
+    if (j0 + 4 >= c.W) {
+      // the thread that holds the row's last pixel (linspace's exact end point): float64 per pixel
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int j = min(j0 + k, c.W - 1);
-      const double dx = j == c.W - 1 ? (c.W == 1 ? x0 : x1) : fma((double)j, sx, x0);
-      const double x = dx * rf;
-      const float xw = (float)fma(x, ax, bx), yw = (float)fma(x, ay, by), zw = (float)fma(x, az, bz);
-      o[k] = -fast_atan2_deg(yw, sqrtf(fmaf(xw, xw, zw * zw)));
+      for (int k = 0; k < 4; ++k) {
+        const int j = min(j0 + k, c.W - 1);
+        const double dx = j == c.W - 1 ? (c.W == 1 ? x0 : x1) : fma((double)j, sx, x0);
+        const double x = dx * rf;
+        const float xw = (float)fma(x, ax, bx), yw = (float)fma(x, ay, by), zw = (float)fma(x, az, bz);
+        o[k] = -fast_atan2_deg(yw, sqrtf(fmaf(xw, xw, zw * zw)));
+      }
+    } else {
+      const double x = fma((double)j0, sx, x0) * rf, xs = sx * rf;          // first pixel and the step between pixels
+      const float xw0 = (float)fma(x, ax, bx), yw0 = (float)fma(x, ay, by), zw0 = (float)fma(x, az, bz);
+      const float dxw = (float)(xs * ax), dyw = (float)(xs * ay), dzw = (float)(xs * az);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float xw = fmaf((float)k, dxw, xw0), yw = fmaf((float)k, dyw, yw0), zw = fmaf((float)k, dzw, zw0);
+        o[k] = -fast_atan2_deg(yw, sqrtf(fmaf(xw, xw, zw * zw)));
+      }
     }
     float* dst = lat + c.lat_off + p0;
     if (nj == 4 && ((c.lat_off + p0) & 3) == 0) __stcs(reinterpret_cast<float4*>(dst), make_float4(o[0], o[1], o[2], o[3]));
@@ -421,6 +441,12 @@ __global__ void __launch_bounds__(256) resize_f32_kernel(const float* __restrict
   const float v00 = __ldg(src + ((long long)y0 * W + x0) * C + c), v01 = __ldg(src + ((long long)y0 * W + x1) * C + c);
   const float v10 = __ldg(src + ((long long)y1 * W + x0) * C + c), v11 = __ldg(src + ((long long)y1 * W + x1) * C + c);
   dst[i] = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
+}
+
+// Write-only bandwidth probe (bench.py: the roofline of the store-bound write-out kernels): 16-byte streaming stores, grid-stride.
+__global__ void __launch_bounds__(256) fill_stream_kernel(float4* __restrict__ dst, long long n4, float v) {
+  const float4 val = make_float4(v, v, v, v);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) __stcs(dst + i, val);
 }
 
 }  // namespace pf

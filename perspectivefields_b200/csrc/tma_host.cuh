@@ -7,6 +7,7 @@
 #include <string>
 
 #include "gemm_tma.cuh"
+#include "gemm2_tma.cuh"
 
 namespace pf {
 
@@ -108,14 +109,12 @@ inline cudaError_t gemm_tma_launch_bn(const TmaMaps& maps, const TmaGemmParams& 
         if (pred) { q.pred_w = pred[g].w; q.pred_b = pred[g].b; q.pred_out = pred[g].out; q.pred_nc = pred[g].nc; q.pred_mode = pred[g].mode; }
         if (cdiv(p.N, BN) > 1) return cudaErrorInvalidValue;   // (not needed by the network: conv_fuse_conv1 has one N tile)
         const unsigned gr = (unsigned)(m_tiles < sm_count ? m_tiles : sm_count);
-        gemm_tma_kernel<BN, MODE, KB><<<gr, kTmaThreads, Cfg::kSmemBytes, st>>>(maps, q, tiles_x, tiles_y);
-        last = cudaGetLastError();
+        last = launch_pdl(gemm_tma_kernel<BN, MODE, KB>, dim3(gr), dim3(kTmaThreads), Cfg::kSmemBytes, st, maps, q, tiles_x, tiles_y);
         if (last != cudaSuccess) return last;
       }
     return last;
   }
-  gemm_tma_kernel<BN, MODE, KB><<<grid, kTmaThreads, Cfg::kSmemBytes, st>>>(maps, p, tiles_x, tiles_y);
-  return cudaGetLastError();
+  return launch_pdl(gemm_tma_kernel<BN, MODE, KB>, dim3(grid), dim3(kTmaThreads), Cfg::kSmemBytes, st, maps, p, tiles_x, tiles_y);
 }
 
 // every instantiation the dispatcher below can reach: X(BN, MODE, KB)
@@ -133,6 +132,65 @@ inline cudaError_t gemm_tma_configure_device() {
   PF_TMA_VARIANTS(PF_TMA_CFG)
 #undef PF_TMA_CFG
   return e;
+}
+
+// ---- CTA-pair GEMM (gemm2_tma.cuh): cluster 2x1x1, one pair per TPC
+#define PF_TMA2_VARIANTS(X) X(256) X(224) X(192) X(160) X(128) X(96) X(64)
+
+struct Gemm2Info { int max_clusters[9]; };   // index BN / 32: concurrently resident pairs on this device (0 = not available)
+inline Gemm2Info& gemm2_info(int device) {
+  static Gemm2Info info[64];
+  return info[device & 63];
+}
+inline cudaError_t gemm2_configure_device(int device, int sm_count) {
+  cudaError_t e = cudaSuccess;
+  Gemm2Info& gi = gemm2_info(device);
+#define PF_TMA2_CFG(BN_)                                                                                                      \
+  if (e == cudaSuccess) {                                                                                                     \
+    e = cudaFuncSetAttribute(gemm2_tma_kernel<BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tma2Cfg<BN_>::kSmemBytes);   \
+    if (e == cudaSuccess) {                                                                                                   \
+      cudaLaunchConfig_t cfg{};                                                                                               \
+      cfg.gridDim = dim3(sm_count & ~1); cfg.blockDim = dim3(kTmaThreads); cfg.dynamicSmemBytes = Tma2Cfg<BN_>::kSmemBytes;   \
+      cudaLaunchAttribute at[1];                                                                                              \
+      at[0].id = cudaLaunchAttributeClusterDimension;                                                                         \
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;                                     \
+      cfg.attrs = at; cfg.numAttrs = 1;                                                                                       \
+      int n = 0;                                                                                                              \
+      if (cudaOccupancyMaxActiveClusters(&n, gemm2_tma_kernel<BN_>, &cfg) != cudaSuccess) { n = 0; (void)cudaGetLastError(); } \
+      gi.max_clusters[BN_ / 32] = n;                                                                                          \
+    }                                                                                                                         \
+  }
+  PF_TMA2_VARIANTS(PF_TMA2_CFG)
+#undef PF_TMA2_CFG
+  return e;
+}
+
+template <int BN>
+inline cudaError_t gemm2_launch_bn(const TmaMaps& maps, const TmaGemmParams& p, int nclusters, cudaStream_t st) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * nclusters); cfg.blockDim = dim3(kTmaThreads); cfg.dynamicSmemBytes = Tma2Cfg<BN>::kSmemBytes; cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, gemm2_tma_kernel<BN>, maps, p);
+}
+// pair tiles of this problem and the number of clusters to launch (0: use the single-CTA kernel)
+inline int gemm2_plan(int device, int M, int N, int bn) {
+  const int avail = gemm2_info(device).max_clusters[bn / 32];
+  if (avail < 1 || bn < 64) return 0;
+  const long long tiles = (long long)cdiv(M, 256) * cdiv(N, bn);
+  if (tiles < avail) return 0;              // too few pair tiles to cover the machine once: 128-row tiles spread better
+  return avail;
+}
+inline cudaError_t gemm2_launch(const TmaMaps& maps, const TmaGemmParams& p, int bn, int nclusters, cudaStream_t st) {
+#define PF_TMA2_CASE(BN_) if (bn == BN_) return gemm2_launch_bn<BN_>(maps, p, nclusters, st);
+  PF_TMA2_VARIANTS(PF_TMA2_CASE)
+#undef PF_TMA2_CASE
+  return cudaErrorInvalidValue;
 }
 
 inline cudaError_t gemm_tma_launch(int mode, const TmaMaps& maps, const TmaGemmParams& p, int bn, int kb, int sm_count, cudaStream_t st,

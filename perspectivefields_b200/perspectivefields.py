@@ -372,15 +372,12 @@ class PerspectiveFields(nn.Module):
             return (2, 1)
         return (self._variant["gravity_classes"], self._variant["latitude_classes"])
 
-    @torch.no_grad()
-    def inference_batch_encoded(self, jpeg_list, max_threads=0):
+    def decode_batch(self, jpeg_list, max_threads=0):
         """Decode front-end: a list of JPEG byte strings (what ``cv2.imread`` would read from disk,
-        demo/demo.py:151) is decoded on the GPU (nvJPEG, BGR interleaved) straight into the device blob the fused pre-process
-        reads; no host-side pixel buffer exists.  Returns the same ``list[dict]`` as ``inference_batch``."""
+        demo/demo.py:151) is decoded on the GPU (nvJPEG, BGR interleaved) into ONE device blob of packed HWC uint8 images -- the
+        layout the fused pre-process reads; no host-side pixel buffer exists.  Returns (blob, offsets, heights, widths)."""
         if self.input_format != "BGR":
             raise NotImplementedError("the decode front-end writes BGR (the reference's INPUT.FORMAT)")
-        if not jpeg_list:
-            return []
         eng = self._get_engine()
         L = eng.L
         with torch.cuda.device(eng.device):
@@ -395,13 +392,27 @@ class PerspectiveFields(nn.Module):
                 _native.check(L.pf_jpeg_info(self._jpeg, b.ctypes.data, b.size, ctypes.byref(h1), ctypes.byref(w1)))
                 hs[i], ws[i] = h1.value, w1.value
             sizes = [hs[i] * ws[i] * 3 for i in range(n)]
-            offs = (ctypes.c_int64 * n)(*np.concatenate([[0], np.cumsum(sizes[:-1])]).astype(np.int64).tolist())
+            offsets = np.zeros(n, np.int64)
+            np.cumsum(sizes[:-1], out=offsets[1:])
+            offs = (ctypes.c_int64 * n)(*offsets.tolist())
             blob = torch.empty(int(sum(sizes)), dtype=torch.uint8, device=eng.device)
             ptrs = (ctypes.c_void_p * n)(*[b.ctypes.data for b in bufs])
             lens = (ctypes.c_int64 * n)(*[b.size for b in bufs])
             stream = torch.cuda.current_stream(eng.device).cuda_stream
             _native.check(L.pf_jpeg_decode_batch(self._jpeg, n, ptrs, lens, hs, ws, blob.data_ptr(), offs, stream))
-            out = eng.forward(n, list(hs), list(ws), blob=blob, offsets=np.asarray(list(offs), np.int64))
+        return blob, offsets, list(hs), list(ws)
+
+    @torch.no_grad()
+    def inference_batch_encoded(self, jpeg_list, max_threads=0):
+        """``inference_batch`` on JPEG byte strings: ``decode_batch`` + the forward on the decoded blob.  Returns the same
+        ``list[dict]`` as ``inference_batch`` (up to the decoder: nvJPEG's IDCT / chroma up-sampling round differently from
+        libjpeg's, so decoded pixels can differ by a few grey levels from ``cv2.imread``)."""
+        if not jpeg_list:
+            return []
+        blob, offsets, hs, ws = self.decode_batch(jpeg_list, max_threads)
+        eng = self._get_engine()
+        with torch.cuda.device(eng.device):
+            out = eng.forward(len(jpeg_list), hs, ws, blob=blob, offsets=offsets)
         return self._assemble(out)
 
     @torch.no_grad()

@@ -189,6 +189,6 @@ def test_fast_asin_and_atan2_polynomials_of_the_kernels():
     for c in ct[1:]:
         p = (p * z + c).astype(f)
     pr = (q + (q * z).astype(f) * p).astype(f)
-    deg = np.copysign((pr.astype(np.float64) * 57.29577951308232 + np.where(hi, 90.0, np.where(mid, 45.0, 0.0))).astype(f), yw)
+    deg = np.copysign((pr.astype(np.float64) * np.float64(f(57.29577951308232)) + np.where(hi, 90.0, np.where(mid, 45.0, 0.0))).astype(f), yw)   # fmaf: one rounding
     ref = np.degrees(np.arctan2(yw.astype(np.float64), h.astype(np.float64)))
     assert np.abs(deg.astype(np.float64) - ref).max() < 1e-5
