@@ -513,7 +513,7 @@ def gather_leg(b, imgs_rank, steps, warmup, micro_batch):
     full = [placeholder] * (world * B)
     full[rank * B:(rank + 1) * B] = imgs_rank
     tr = pfdist.PfCommTransport(b.dev)
-    res = None
+    res, ev, prev = None, None, None
     for _ in range(max(warmup, 1)):
         res = pfdist.inference_batch_sharded(b.model, full, gather_to=0, micro_batch=micro_batch, transport=tr)
     b.barrier()
@@ -523,9 +523,17 @@ def gather_leg(b, imgs_rank, steps, warmup, micro_batch):
     e0.record()
     for _ in range(steps):
         b.flush.fill_(1)
-        res = pfdist.inference_batch_sharded(b.model, full, gather_to=0, micro_batch=micro_batch, transport=tr)
+        # pipelined calls (wait=False): the gather of step k overlaps the forward of step k+1; the results of step k are released
+        # only after their event has completed (two steps in flight), and the last gather is inside the timed region
+        res, ev = pfdist.inference_batch_sharded(b.model, full, gather_to=0, micro_batch=micro_batch, transport=tr, wait=False)
+        if prev is not None:
+            prev[1].synchronize()
+        prev = (res, ev)
+    torch.cuda.current_stream(b.dev).wait_event(ev)
     e1.record()
     b.barrier()
+    res = prev[0]
+    prev = None
     wall_ms = (time.perf_counter() - tw) * 1000
     ms = b.max_over_ranks(max(e0.elapsed_time(e1), wall_ms))
     moved = tr.bytes_moved - moved0
@@ -533,7 +541,8 @@ def gather_leg(b, imgs_rank, steps, warmup, micro_batch):
     del res
     tr.close()
     out = {"value": world * B * steps / (ms / 1000.0), "unit": "images/s", "ms_per_step": ms / steps, "micro_batch": micro_batch,
-           "images_per_call": world * B, "transport": "pf_gather: grouped ncclSend/ncclRecv from libpf_b200.so on a side stream, inside the timed region"}
+           "images_per_call": world * B, "transport": "pf_gather: grouped ncclSend/ncclRecv from libpf_b200.so on a side stream, inside the timed region; calls pipelined (the "
+                        "gather of step k overlaps the forward of step k+1, receives posted after the root's own forward)"}
     if rank == 0:
         out.update({"bytes_received_per_step_rank0": moved / steps, "achieved_gbs_into_rank0": moved / (ms / 1000.0) / 1e9,
                     "results_on_rank0": n_back,

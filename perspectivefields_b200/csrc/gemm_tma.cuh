@@ -78,10 +78,18 @@ template <int BN, int MODE, int KB> struct TmaCfg {
   static constexpr int kStagesRaw = kBudget / kStage;
   static constexpr int kStages = kStagesRaw > 16 ? 16 : kStagesRaw;
   static constexpr int kSmemBytes = (MODE == MODE_HALO ? 2 * kABuf : 0) + kStages * kStage + kEpiStage + kEpiVec + 512 + 1024;
-  static constexpr int kTmemCols = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+  // Narrow halo tiles (BN <= 128): every tcgen05.mma narrower than N ~ 192 costs the same ~93 cycles (it is bound by reading its
+  // 128 x 16 A slice from shared memory), so the three MMAs per product are folded into TWO: a_hi x [b_hi ; b_lo] as ONE MMA of
+  // width 2 BN (the hi and lo weight planes of a pipeline step are adjacent in shared memory) into an accumulator pair
+  // (D1 | D2), and a_lo x b_hi into D1; the epilogue adds D1 + D2.  Same products, one A-slice read less per K step.
+  static constexpr bool kDual = MODE == MODE_HALO && BN <= 128;
+  static constexpr int kAccCols = kDual ? 2 * BN : BN;            // TMEM columns of one accumulator
+  static constexpr int kTmemCols = 2 * kAccCols <= 32 ? 32 : (2 * kAccCols <= 64 ? 64 : (2 * kAccCols <= 128 ? 128 : (2 * kAccCols <= 256 ? 256 : 512)));
   static constexpr uint32_t kIdesc = umma_idesc_bf16(BN);
+  static constexpr uint32_t kIdesc2 = umma_idesc_bf16(2 * BN <= 256 ? 2 * BN : 256);
   static_assert(kStages >= 3, "ring too shallow");
-  static_assert(2 * BN <= 512, "two accumulators must fit TMEM");
+  static_assert(2 * kAccCols <= 512, "two accumulators must fit TMEM");
+  static_assert(!kDual || kBPlane % 1024 == 0, "dual-N: the lo plane must continue the hi plane's swizzle pattern");
 };
 
 // K-major operand descriptor for a tile whose rows are KB bf16 wide (KB = 32: SWIZZLE_64B, 8-row groups 512 B apart;
@@ -241,7 +249,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
       const int as = tl & 1;
       if (p.dbg & 256) mbar_wait_spin(tmem_empty(as), ((tl >> 1) & 1) ^ 1); else mbar_wait(tmem_empty(as), ((tl >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator
       tc_fence_after();
-      const uint32_t acc = tmem + (uint32_t)(as * BN);
+      const uint32_t acc = tmem + (uint32_t)(as * Cfg::kAccCols);
       for (int kc = 0; kc < nk; ++kc, ++it) {
         const int s = it % NS;
         uint32_t a_hi, a_lo;
@@ -274,9 +282,14 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
 #pragma unroll
           for (int kk = 0; kk < KB / 16; ++kk) {
             if (MODE == MODE_GEMM && (p.dbg & 4)) break;
-            umma_bf16(acc, dal, dbh, Cfg::kIdesc, (kc | kk) ? 1u : 0u);
-            umma_bf16(acc, dah, dbl, Cfg::kIdesc, 1u);
-            umma_bf16(acc, dah, dbh, Cfg::kIdesc, 1u);
+            if (Cfg::kDual) {
+              umma_bf16(acc, dah, dbh, Cfg::kIdesc2, (kc | kk) ? 1u : 0u);     // (D1 | D2) (+)= a_hi x [b_hi ; b_lo]
+              umma_bf16(acc, dal, dbh, Cfg::kIdesc, 1u);                       //  D1        += a_lo x b_hi
+            } else {
+              umma_bf16(acc, dal, dbh, Cfg::kIdesc, (kc | kk) ? 1u : 0u);
+              umma_bf16(acc, dah, dbl, Cfg::kIdesc, 1u);
+              umma_bf16(acc, dah, dbh, Cfg::kIdesc, 1u);
+            }
             dah += 2; dal += 2; dbh += 2; dbl += 2;
           }
           if (!b_resident) umma_commit(empty_b(s));
@@ -335,7 +348,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = (uint32_t)(lane + j);
           } else {
-            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + ch * 32), v);
+            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * Cfg::kAccCols + ch * 32), v);
           }
           if (!warp_active) continue;                                  // whole warp beyond the matrix (warp-uniform)
           const int ob = cc & 1;
@@ -452,7 +465,13 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
 #pragma unroll 1
       for (int ch = eh; ch < BN / 32; ch += 2) {
         uint32_t v[32];
-        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + ch * 32), v);
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * Cfg::kAccCols + ch * 32), v);
+        if (Cfg::kDual) {       // second half of the accumulator pair: the a_hi x b_lo products
+          uint32_t v2[32];
+          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * Cfg::kAccCols + BN + ch * 32), v2);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+        }
         const int nb = n0 + ch * 32;
         const bool ph4 = MODE == MODE_HALO && BN == 128 && p.phase4;
         // output row / first output column of this chunk (phase mode: hi-res pixel of phase `ch`, channels 0-31)

@@ -234,7 +234,10 @@ inline cudaError_t attention_launch(const float* q, const float* kv, float* out,
 // =====================================================================================================
 // Depthwise 3x3 conv (pad 1) + bias + GELU(erf) on NHWC -- Mix-FFN middle, mix_transformers.py:51-52,502-508.
 // w: [9][C], thread = 4 channels of one pixel.
-__global__ void __launch_bounds__(256) dwconv3x3_gelu_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C,
+#ifndef PF_DW3_MINBLOCKS
+#define PF_DW3_MINBLOCKS 2     // (3 blocks per SM = 80 registers with spills measured 4 % slower, A/B in profiles/r02_notes.md)
+#endif
+__global__ void __launch_bounds__(256, PF_DW3_MINBLOCKS) dwconv3x3_gelu_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C,
                                                              const float* __restrict__ w, const float* __restrict__ bias,
                                                              __nv_bfloat16* __restrict__ shi = nullptr, __nv_bfloat16* __restrict__ slo = nullptr) {
   pdl_wait();

@@ -12,6 +12,8 @@ stream, so the transfer of micro-batch k overlaps the forward of micro-batch k+1
 * ``TorchTransport``: ``torch.distributed.batch_isend_irecv`` (gloo on CPU in the tests; also works with the NCCL backend).
 """
 import ctypes
+import os
+import time
 
 import numpy as np
 import torch
@@ -137,11 +139,19 @@ def _sizes(imgs):
     return [(int(im.shape[0]), int(im.shape[1])) for im in imgs]
 
 
-def inference_batch_sharded(model, img_bgr_list, gather_to=0, group=None, micro_batch=32, transport=None):
+def inference_batch_sharded(model, img_bgr_list, gather_to=0, group=None, micro_batch=32, transport=None, wait=True):
     """Every rank passes the SAME list; rank r runs the model on its shard, ``micro_batch`` images at a time.  With ``gather_to``
     = a rank, that rank returns the full ``list[dict]`` in input order (tensors on its device) and the other ranks return their
     own shard's results; with ``gather_to=None`` nothing is exchanged.  ``transport``: a ``PfCommTransport`` / ``TorchTransport``
     to reuse across calls (default: a ``TorchTransport`` on ``group``).
+
+    ``wait=False`` (pipelined calls): the caller's stream is NOT made to wait for the transfers; the function returns
+    ``(results, event)`` and the caller waits on ``event`` (recorded on the side stream) before touching gathered tensors -- the
+    gather of call k then overlaps the forward of call k+1.
+
+    The receives of a round are posted only after the gathering rank's OWN forward of that round has finished: an NCCL receive
+    kernel posted earlier would sit on its SMs spinning for the peers' data while the forward's persistent kernels (one
+    225 KB-shared-memory CTA per SM) need every SM (measured: +30 % on the root's step, profiles/r02_notes.md).
 
     ``model`` provides ``infer_raw(imgs) -> raw`` (the five output blobs of one micro-batch + host metadata),
     ``assemble_raw(raw) -> list[dict]`` and ``out_classes()`` (``PerspectiveFields`` does)."""
@@ -166,13 +176,24 @@ def inference_batch_sharded(model, img_bgr_list, gather_to=0, group=None, micro_
     rounds = max(len(micro_batches(a, b, micro_batch)) for a, b in bounds)
     results = [None] * n
     keep = []
+    trace = {} if os.environ.get("PF_DIST_TRACE") else None
+    t_ = time.perf_counter()
+
+    def lap(name):
+        nonlocal t_
+        if trace is not None:
+            now = time.perf_counter()
+            trace[name] = trace.get(name, 0.0) + (now - t_) * 1000
+            t_ = now
     for k in range(rounds):
         raw = None
         if k < len(my_mbs):
             a, b = my_mbs[k]
             raw = model.infer_raw(img_bgr_list[a:b])
+            lap("infer_raw")
             for i, d in zip(range(a, b), model.assemble_raw(raw)):
                 results[i] = d
+            lap("assemble_own")
         # exchange of round k on the side stream, after this rank's forward of round k; the next round's forward (enqueued on
         # the compute stream by the next loop iteration) overlaps it
         done = None
@@ -182,6 +203,8 @@ def inference_batch_sharded(model, img_bgr_list, gather_to=0, group=None, micro_
         if rank == gather_to:
             bufs, peers, metas = [], [], []
             ctx = torch.cuda.stream(side) if on_gpu else _Null()
+            if on_gpu:
+                side.wait_event(done)            # (see the docstring: no receive kernel while this rank's forward runs)
             with ctx:
                 for r, (ra, rb) in enumerate(bounds):
                     mbs = micro_batches(ra, rb, micro_batch)
@@ -193,26 +216,36 @@ def inference_batch_sharded(model, img_bgr_list, gather_to=0, group=None, micro_
                         bufs.append(recv[key])
                         peers.append(r)
                     metas.append((a, b, recv))
+                lap("alloc_recv")
                 tr.exchange(gather_to, bufs, peers, side)
+                lap("exchange_call")
             for a, b, recv in metas:
                 for i, d in zip(range(a, b), model.assemble_raw(recv)):
                     results[i] = d
                 if on_gpu:
                     for key in _BLOBS:
                         recv[key].record_stream(cur)     # allocated on the side stream, consumed by the caller on `cur`
+            lap("assemble_remote")
         elif raw is not None:
             if on_gpu:
                 side.wait_event(done)
             tr.exchange(gather_to, [raw[key] for key in _BLOBS], None, side)
+            lap("exchange_call")
             keep.append(raw)
             if on_gpu:
                 for key in _BLOBS:
                     raw[key].record_stream(side)
+    ev = None
     if on_gpu:
-        cur.wait_stream(side)    # the caller's stream sees complete results
-    if rank == gather_to:
-        return results
-    return [results[i] for i in range(lo, hi)]
+        if wait:
+            cur.wait_stream(side)    # the caller's stream sees complete results
+        else:
+            ev = torch.cuda.Event()
+            ev.record(side)
+    if trace is not None:
+        print(f"[pf dist rank {rank}] host ms: " + ", ".join(f"{k} {v:.2f}" for k, v in trace.items()), flush=True)
+    out = results if rank == gather_to else [results[i] for i in range(lo, hi)]
+    return out if wait else (out, ev)
 
 
 class _Null:

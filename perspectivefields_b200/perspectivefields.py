@@ -434,25 +434,28 @@ class PerspectiveFields(nn.Module):
         perspectivefields.py:261-271."""
         v = self._variant
         n = out["pred_gravity"].shape[0]
+        # one unbind / split call per output tensor (not ~12 tensor operations per image: at 256 images per call the per-image
+        # Python work was several milliseconds)
+        hs, ws = [int(x) for x in out["h"]], [int(x) for x in out["w"]]
+        pg, pl = out["pred_gravity"].unbind(0), out["pred_latitude"].unbind(0)
+        if len(set(zip(hs, ws))) == 1:
+            go_ = out["gravity_original"].view(n, 2, hs[0], ws[0]).unbind(0)
+            lo_ = out["latitude_original"].view(n, hs[0], ws[0]).unbind(0)
+        else:
+            go_ = [t.view(2, h, w) for t, h, w in zip(out["gravity_original"].split([2 * h * w for h, w in zip(hs, ws)]), hs, ws)]
+            lo_ = [t.view(h, w) for t, h, w in zip(out["latitude_original"].split([h * w for h, w in zip(hs, ws)]), hs, ws)]
+        cols = [c.unbind(0) for c in out["params"].t().unbind(0)] if v["param_net"] else None     # cols[j][i] = params[i, j] (0-dim views)
+        zeros = torch.zeros_like(out["params"][:, 0]).unbind(0) if v["param_net"] == "ParamNet" else None
         res = []
-        P = out["params"]
-        zeros = torch.zeros_like(P[:, 0]) if v["param_net"] == "ParamNet" else None
         for i in range(n):
-            h, w = int(out["h"][i]), int(out["w"][i])
-            go, lo = int(out["g_off"][i]), int(out["l_off"][i])
-            d = {
-                "pred_gravity": out["pred_gravity"][i],
-                "pred_gravity_original": out["gravity_original"][go:go + 2 * h * w].view(2, h, w),
-                "pred_latitude": out["pred_latitude"][i],
-                "pred_latitude_original": out["latitude_original"][lo:lo + h * w].view(h, w),
-                "pred_latitude_original_mode": "deg",
-            }
+            d = {"pred_gravity": pg[i], "pred_gravity_original": go_[i], "pred_latitude": pl[i], "pred_latitude_original": lo_[i],
+                 "pred_latitude_original_mode": "deg"}
             if v["param_net"] == "ParamNet":
-                d.update({"pred_roll": P[i, 0], "pred_pitch": P[i, 1], "pred_vfov": P[i, 2], "pred_rel_focal": P[i, 5],
-                          "pred_general_vfov": P[i, 2], "pred_rel_cx": zeros[i], "pred_rel_cy": zeros[i]})
+                d.update({"pred_roll": cols[0][i], "pred_pitch": cols[1][i], "pred_vfov": cols[2][i], "pred_rel_focal": cols[5][i],
+                          "pred_general_vfov": cols[2][i], "pred_rel_cx": zeros[i], "pred_rel_cy": zeros[i]})
             elif v["param_net"] == "ParamNetConvNextRegress":
-                d.update({"pred_roll": P[i, 0], "pred_pitch": P[i, 1], "pred_general_vfov": P[i, 2], "pred_rel_cx": P[i, 3],
-                          "pred_rel_cy": P[i, 4], "pred_rel_focal": P[i, 5]})
+                d.update({"pred_roll": cols[0][i], "pred_pitch": cols[1][i], "pred_general_vfov": cols[2][i], "pred_rel_cx": cols[3][i],
+                          "pred_rel_cy": cols[4][i], "pred_rel_focal": cols[5][i]})
             res.append(d)
         return res
 
