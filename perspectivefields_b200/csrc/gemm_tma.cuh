@@ -72,8 +72,13 @@ template <int BN, int MODE, int KB> struct TmaCfg {
   // MODE_GEMM epilogue staging, 64 KB: warps 4-11 (two per TMEM lane quarter, alternate 32-column chunks), each two 4 KB tiles
   // (32 rows x 32 columns fp32, or bf16 hi + lo) that receive the residual tile (TMA load) and send the result (TMA store).
   // Plus bias / layer-scale copies (2 x 256 floats per warp).
+#ifdef PF_PROBE_DEEP_RING   // pipeline-depth experiment (tests/diag/gemm_dbg_probe.py with dbg bit 7): no epilogue staging, all smem to the ring
+  static constexpr int kEpiStage = 0;
+  static constexpr int kEpiVec = 0;
+#else
   static constexpr int kEpiStage = MODE == MODE_GEMM ? 4 * 16384 : 0;
   static constexpr int kEpiVec = MODE == MODE_GEMM ? 8 * 2 * 256 * 4 : 0;
+#endif
   static constexpr int kBudget = 225 * 1024 - kEpiStage - kEpiVec - (MODE == MODE_HALO ? 2 * kABuf : 0);
   static constexpr int kStagesRaw = kBudget / kStage;
   static constexpr int kStages = kStagesRaw > 16 ? 16 : kStagesRaw;
@@ -87,7 +92,7 @@ template <int BN, int MODE, int KB> struct TmaCfg {
   static constexpr int kTmemCols = 2 * kAccCols <= 32 ? 32 : (2 * kAccCols <= 64 ? 64 : (2 * kAccCols <= 128 ? 128 : (2 * kAccCols <= 256 ? 256 : 512)));
   static constexpr uint32_t kIdesc = umma_idesc_bf16(BN);
   static constexpr uint32_t kIdesc2 = umma_idesc_bf16(2 * BN <= 256 ? 2 * BN : 256);
-  static_assert(kStages >= 3, "ring too shallow");
+  static_assert(kStages >= 2, "ring too shallow");
   static_assert(2 * kAccCols <= 512, "two accumulators must fit TMEM");
   static_assert(!kDual || kBPlane % 1024 == 0, "dual-N: the lo plane must continue the hi plane's swizzle pattern");
 };

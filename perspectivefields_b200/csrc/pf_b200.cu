@@ -143,6 +143,12 @@ struct pf_engine {
   GemmW conv0, conv1;
   GemmW conv1p;                       // conv_fuse_conv1 composed with the x2 upsample in front of it: 4 phases x 32 outputs per head
   const float *conv1f_w, *conv1f_b;   // plain fp32 conv_fuse_conv1 [head][tap][ci][o] / bias, for the border-ring kernel
+  bool use_fork = false;              // option "fork": the spatial-reduction branch of a MiT block (sr conv -> LayerNorm -> kv) runs on a second
+                                      // stream next to the q projection (both only depend on LayerNorm 1; their grids leave SMs idle: 50-75 tiles).
+                                      // Default OFF: measured 1 % slower (the persistent kernels of the two streams compete for SMs and the
+                                      // event waits break the programmatic-dependent-launch chain; profiles/r02_notes.md)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool use_pair = true;               // option "pair": GEMM-mode launches with enough tiles run on CTA pairs (gemm2_tma.cuh, cta_group::2)
   bool use_dwln = false;              // option "dw_ln": ConvNeXt depthwise 7x7 fused with the LayerNorm that follows it
   bool use_pdl = true;                // option "pdl": programmatic dependent launch of the graph's kernels (common.cuh)
@@ -780,11 +786,26 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
       else TRY(F.ln_split(x, t1, rows, C, b.ln1, 1e-6f));
       Epi oq, okv;
       if (qkv_split) { oq.S = q; okv.S = kv; } else { oq.C = qf; oq.ldc = C; okv.C = kvf; okv.ldc = 2 * C; }
-      TRY(F.tgemm(t1, rows, C, 0, b.q, C, oq));
+      // q and the spatial-reduction branch both depend on LayerNorm 1 only: fork the branch onto the engine's side stream (its
+      // GEMMs have 50-75 tiles for 148 SMs; q's second, partial wave leaves SMs idle as well) and join before the attention core
+      const bool fork = !dry && sr > 1 && e->use_fork && e->side && !e->kp.on && !e->profile && !sync_debug() && !e->debug;
+      if (fork) {
+        CU(cudaEventRecord(e->ev_fork, st));
+        CU(cudaStreamWaitEvent(e->side, e->ev_fork, 0));
+        F.st = e->side;
+      }
       if (sr > 1) {
         { Epi o; o.C = t2f; o.ldc = C; TRY(F.tgemm(t1p, (long long)n * 100, sr * sr * C, 0, b.sr, C, o)); }
         TRY(F.ln_split(t2f, t2, (long long)n * 100, C, b.srln, 1e-5f));
         TRY(F.tgemm(t2, (long long)n * 100, C, 0, b.kv, 2 * C, okv));
+      }
+      if (fork) {
+        CU(cudaEventRecord(e->ev_join, e->side));
+        F.st = st;
+      }
+      TRY(F.tgemm(t1, rows, C, 0, b.q, C, oq));
+      if (fork) CU(cudaStreamWaitEvent(st, e->ev_join, 0));
+      if (sr > 1) {
       } else {
         TRY(F.tgemm(t1, rows, C, 0, b.kv, 2 * C, okv));
       }
@@ -1003,6 +1024,12 @@ int pf_create(int device, const pf_model_desc* desc, pf_handle* out) {
     delete e;
     return r;
   }
+  if (cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+    const int r = fail(PF_ERR_CUDA, "pf_create: side stream / events: %s", cudaGetErrorString(cudaGetLastError()));
+    pf_destroy(e);
+    return r;
+  }
   *out = e;
   return PF_OK;
 }
@@ -1010,6 +1037,9 @@ int pf_create(int device, const pf_model_desc* desc, pf_handle* out) {
 int pf_destroy(pf_handle h) {
   if (!h) return PF_OK;
   cudaSetDevice(h->device);
+  if (h->side) { cudaStreamSynchronize(h->side); cudaStreamDestroy(h->side); }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   cudaFree(h->table_dev);
   cudaFreeHost(h->table_host);
   for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -1144,6 +1174,7 @@ int pf_set_option(pf_handle h, const char* name, int value) {
   if (!strcmp(name, "pdl")) { h->use_pdl = value != 0; return PF_OK; }
   if (!strcmp(name, "dw_ln")) { h->use_dwln = value != 0; return PF_OK; }
   if (!strcmp(name, "pair")) { h->use_pair = value != 0; return PF_OK; }
+  if (!strcmp(name, "fork")) { h->use_fork = value != 0; return PF_OK; }
   return fail(PF_ERR_ARG, "pf_set_option: unknown option '%s'", name);
 }
 // out[cfg*3 + {0,1,2}] = {milliseconds, algorithmic FLOPs, launches} per GEMM engine configuration (7 configs),

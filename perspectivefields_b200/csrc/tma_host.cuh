@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <string>
 
 #include "gemm_tma.cuh"
@@ -82,7 +83,11 @@ inline int tma_pick_bn(int N, int mode) {
 
 // K elements per pipeline step: 64 for narrow tiles when K allows it (halo mode: BN <= 128; GEMM mode, whose stages also
 // hold the A tile and whose epilogue staging takes 72 KB: BN <= 64), else 32
-inline int tma_pick_kb(int bn, int K, int mode) { return (bn <= (mode == MODE_HALO ? 128 : 64) && K % 64 == 0) ? 64 : 32; }
+inline int tma_pick_kb(int bn, int K, int mode) {
+  static const int wide = getenv("PF_KB64") ? atoi(getenv("PF_KB64")) : 0;     // experiment: 128-byte TMA rows for wider GEMM-mode tiles
+  const int lim = mode == MODE_HALO ? 128 : (wide ? wide : 64);
+  return (bn <= lim && K % 64 == 0) ? 64 : 32;
+}
 
 struct PredTail { const float* w; const float* b; float* out; int nc, mode; };   // per group, see TmaGemmParams::pred_*
 
@@ -121,6 +126,7 @@ inline cudaError_t gemm_tma_launch_bn(const TmaMaps& maps, const TmaGemmParams& 
 #define PF_TMA_VARIANTS(X)                                                                                                  \
   X(256, MODE_GEMM, 32) X(224, MODE_GEMM, 32) X(192, MODE_GEMM, 32) X(160, MODE_GEMM, 32) X(128, MODE_GEMM, 32) X(96, MODE_GEMM, 32) \
   X(64, MODE_GEMM, 32) X(32, MODE_GEMM, 32) X(64, MODE_GEMM, 64) X(32, MODE_GEMM, 64)                                        \
+  X(96, MODE_GEMM, 64) X(128, MODE_GEMM, 64) X(160, MODE_GEMM, 64)                                                           \
   X(256, MODE_HALO, 32) X(128, MODE_HALO, 64) X(64, MODE_HALO, 64) X(32, MODE_HALO, 64)
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute: called once for every device an engine is
