@@ -105,7 +105,9 @@ int pf_profile_kernels_read(pf_handle h, char* buf, int cap);
 
 /* Engine options (all default 1 unless noted; the whole graph runs on the persistent TMA -> tcgen05 -> TMEM engine with pre-split
  * bf16 hi/lo activations, gemm_tma.cuh):
- * "attn_mma": attention core on the tensor cores (attention_mma.cuh) instead of the exact-softmax CUDA-core kernel.
+ * "attn_tc": attention core on tcgen05 / TMEM (attention_tc.cuh: S = Q K^T into TMEM, softmax one thread per row from TMEM, P V as a
+ *   second MMA with V consumed MN-major); 0 = the warp-level mma.sync kernel (attention_mma.cuh).
+ * "attn_mma": (with "attn_tc" = 0) mma.sync attention core instead of the exact-softmax CUDA-core kernel.
  * "attn_split": q / kv leave their GEMMs as split planes (0 = fp32, split inside the attention kernel).
  * "stem_tc": the two 7x7 stems as patch gather + TMA GEMM instead of fp32 direct convolution.
  * "phase_conv1": conv_fuse_conv1 composed with the x2 bilinear upsample in front of it (four output phases on the 160x160 grid
@@ -174,7 +176,8 @@ int pf_op_conv_gemm(const float* x, int B, int H, int W, int Cin, const void* wh
                     float* y, void* stream);
 int pf_op_layernorm(const float* x, float* y, int64_t rows, int C, const float* w, const float* b, float eps, void* stream);
 int pf_op_attention(const float* q, const float* kv, float* out, int B, int N, int C, int heads, void* stream);      /* CUDA-core fp32 */
-int pf_op_attention_mma(const float* q, const float* kv, float* out, int B, int N, int C, int heads, void* stream);  /* tensor cores, bf16x3 */
+int pf_op_attention_mma(const float* q, const float* kv, float* out, int B, int N, int C, int heads, void* stream);  /* warp-level mma.sync, bf16x3 */
+int pf_op_attention_tc(const float* q, const float* kv, float* out, int B, int N, int C, int heads, void* stream);   /* tcgen05 / TMEM, bf16x3 (default) */
 int pf_op_dwconv3x3_gelu(const float* x, float* y, int B, int H, int W, int C, const float* w9c, const float* bias, void* stream);
 int pf_op_dwconv7x7(const float* x, float* y, int B, int H, int W, int C, const float* w49c, const float* bias, void* stream);
 int pf_op_upsample2x(const float* x, float* y, int B, int H, int W, int C, void* stream);

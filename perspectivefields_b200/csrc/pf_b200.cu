@@ -143,6 +143,7 @@ struct pf_engine {
   GemmW conv0, conv1;
   GemmW conv1p;                       // conv_fuse_conv1 composed with the x2 upsample in front of it: 4 phases x 32 outputs per head
   const float *conv1f_w, *conv1f_b;   // plain fp32 conv_fuse_conv1 [head][tap][ci][o] / bias, for the border-ring kernel
+  bool use_attn_tc = true;            // option "attn_tc": attention core on tcgen05 / TMEM (attention_tc.cuh); 0 = warp-level mma.sync kernel
   bool use_fork = false;              // option "fork": the spatial-reduction branch of a MiT block (sr conv -> LayerNorm -> kv) runs on a second
                                       // stream next to the q projection (both only depend on LayerNorm 1; their grids leave SMs idle: 50-75 tiles).
                                       // Default OFF: measured 1 % slower (the persistent kernels of the two streams compete for SMs and the
@@ -527,6 +528,20 @@ struct Fwd {
     LAUNCHED(layernorm_launch(x, yf, rows, C, w.w, w.b, eps, st, y));
     return PF_OK;
   }
+  // attention core on tcgen05: q [n*N, C] and kv [n*100, 2C] split planes -> a split planes
+  int attention_tc(const SplitT& q, const SplitT& kv, const SplitT& a, int nimg, int N, int C, int heads) {
+    if (dry) return PF_OK;
+    if (q.ld != C || kv.ld != 2 * C || a.ld != C || C != heads * kAtcD) return fail(PF_ERR_ARG, "attention_tc: layout");
+    AtcMaps maps{};
+    const char* msg = nullptr;
+    if (!msg) msg = map2d(&maps.q_hi, q.hi, C, (long long)nimg * N, C, 128, 64);
+    if (!msg) msg = map2d(&maps.q_lo, q.lo, C, (long long)nimg * N, C, 128, 64);
+    if (!msg) msg = map2d(&maps.kv_hi, kv.hi, 2 * C, (long long)nimg * kAtcKeys, 2 * C, kAtcKeysPad, 64);
+    if (!msg) msg = map2d(&maps.kv_lo, kv.lo, 2 * C, (long long)nimg * kAtcKeys, 2 * C, kAtcKeysPad, 64);
+    if (msg) return fail(PF_ERR_CUDA, "%s", msg);
+    LAUNCHED(attention_tc_launch(maps, a.hi, a.lo, nimg, N, C, heads, e->sm_count, st));
+    return PF_OK;
+  }
   // LayerNorm whose output is (also) written in patch order for a k = s = sr convolution on the R x R map (y may be empty)
   int ln_split_patch(const float* x, const SplitT& y, const SplitT& patch, long long rows, int C, const LnW& w, float eps, int R, int sr) {
     if (dry) return PF_OK;
@@ -809,7 +824,9 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
       } else {
         TRY(F.tgemm(t1, rows, C, 0, b.kv, 2 * C, okv));
       }
-      if (!dry) {
+      if (qkv_split && e->use_attn_tc) {
+        TRY(F.attention_tc(q, kv, a, n, N, C, heads));
+      } else if (!dry) {
         if (qkv_split) LAUNCHED(attention_mma_launch(nullptr, nullptr, nullptr, n, N, C, heads, st, a, q, kv));
         else if (e->use_attn_mma) LAUNCHED(attention_mma_launch(qf, kvf, nullptr, n, N, C, heads, st, a));
         else LAUNCHED(attention_launch(qf, kvf, nullptr, n, N, C, heads, st, a));
@@ -986,6 +1003,7 @@ static int configure_device(int device) {
     CU(gemm2_configure_device(device, prop.multiProcessorCount));
   }
   CU(attention_mma_configure_device());
+  CU(attention_tc_configure_device());
   CU(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
   CU(cudaFuncSetAttribute(conv1_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingSmem));
   CU(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPreMaxSmemRows * kNet * 3));
@@ -1175,6 +1193,7 @@ int pf_set_option(pf_handle h, const char* name, int value) {
   if (!strcmp(name, "dw_ln")) { h->use_dwln = value != 0; return PF_OK; }
   if (!strcmp(name, "pair")) { h->use_pair = value != 0; return PF_OK; }
   if (!strcmp(name, "fork")) { h->use_fork = value != 0; return PF_OK; }
+  if (!strcmp(name, "attn_tc")) { h->use_attn_tc = value != 0; return PF_OK; }
   return fail(PF_ERR_ARG, "pf_set_option: unknown option '%s'", name);
 }
 // out[cfg*3 + {0,1,2}] = {milliseconds, algorithmic FLOPs, launches} per GEMM engine configuration (7 configs),
@@ -1514,6 +1533,37 @@ int pf_op_attention_mma(const float* q, const float* kv, float* out, int B, int 
   if (C != heads * kAmD) return fail(PF_ERR_ARG, "pf_op_attention_mma: head_dim must be 64");
   LAUNCHED(attention_mma_launch(q, kv, out, B, N, C, heads, (cudaStream_t)stream));
   return PF_OK;
+}
+int pf_op_attention_tc(const float* q, const float* kv, float* out, int B, int N, int C, int heads, void* stream) {
+  if (!q || !kv || !out || C != heads * kAtcD) return fail(PF_ERR_ARG, "pf_op_attention_tc: head_dim must be 64");
+  TRY(configure_current_device());
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, dev));
+  pf_engine tmp;
+  tmp.device = dev;
+  tmp.sm_count = prop.multiProcessorCount;
+  const long long nq = (long long)B * N * C, nkv = (long long)B * kAtcKeys * 2 * C;
+  char* scratch = nullptr;
+  CU(cudaMalloc(&scratch, (2 * nq + nkv) * 4 + 8192));
+  Fwd F{&tmp, Arena{}, st, false, B};
+  F.ar.base = scratch; F.ar.cap = (2 * nq + nkv) * 4 + 8192;
+  SplitT qs = F.salloc((long long)B * N, C), kvs = F.salloc((long long)B * kAtcKeys, 2 * C), as = F.salloc((long long)B * N, C);
+  int r = PF_OK;
+  cudaError_t le = (split_kernel<<<(unsigned)cdivl(nq, 256), 256, 0, st>>>(q, qs.hi, qs.lo, nq, 0), cudaGetLastError());
+  if (le == cudaSuccess) le = (split_kernel<<<(unsigned)cdivl(nkv, 256), 256, 0, st>>>(kv, kvs.hi, kvs.lo, nkv, 0), cudaGetLastError());
+  if (le != cudaSuccess) r = fail(PF_ERR_CUDA, "split_kernel: %s", cudaGetErrorString(le));
+  if (r == PF_OK) r = F.attention_tc(qs, kvs, as, B, N, C, heads);
+  if (r == PF_OK) {
+    le = (merge_split_kernel<<<(unsigned)cdivl(nq, 256), 256, 0, st>>>(as.hi, as.lo, out, nq), cudaGetLastError());
+    if (le != cudaSuccess) r = fail(PF_ERR_CUDA, "merge_split_kernel: %s", cudaGetErrorString(le));
+  }
+  cudaError_t se = cudaStreamSynchronize(st);
+  cudaFree(scratch);
+  if (r == PF_OK && se != cudaSuccess) r = fail(PF_ERR_CUDA, "pf_op_attention_tc: %s", cudaGetErrorString(se));
+  return r;
 }
 int pf_op_dwconv3x3_gelu(const float* x, float* y, int B, int H, int W, int C, const float* w, const float* bias, void* stream) {
   if (C % 4) return fail(PF_ERR_ARG, "C %% 4");

@@ -9,6 +9,7 @@
 
 #include "gemm_tma.cuh"
 #include "gemm2_tma.cuh"
+#include "attention_tc.cuh"
 
 namespace pf {
 
@@ -138,6 +139,19 @@ inline cudaError_t gemm_tma_configure_device() {
   PF_TMA_VARIANTS(PF_TMA_CFG)
 #undef PF_TMA_CFG
   return e;
+}
+
+// ---- attention core on tcgen05 (attention_tc.cuh)
+inline cudaError_t attention_tc_configure_device() {
+  return cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtcSmemBytes);
+}
+inline cudaError_t attention_tc_launch(const AtcMaps& maps, __nv_bfloat16* ohi, __nv_bfloat16* olo, int B, int N, int C, int heads, int sm_count,
+                                       cudaStream_t st) {
+  const int total = B * heads * cdiv(N, 128);
+  int grid = total < sm_count ? total : sm_count;
+  const int ipc = cdiv(total, grid);          // contiguous items per CTA: K / V of an (image, head) are loaded once per CTA that touches it
+  grid = cdiv(total, ipc);
+  return launch_pdl(attention_tc_kernel, dim3(grid), dim3(kAtcThreads), kAtcSmemBytes, st, maps, ohi, olo, B, N, C, heads, total, ipc);
 }
 
 // ---- CTA-pair GEMM (gemm2_tma.cuh): cluster 2x1x1, one pair per TPC

@@ -73,7 +73,7 @@ def test_layernorm(C):
     assert U.rel_err(y, F.layer_norm(x.double(), (C,), w.double(), b.double(), 1e-6)) < 1e-5
 
 
-@pytest.mark.parametrize("engine", ["fp32", "mma"])
+@pytest.mark.parametrize("engine", ["fp32", "mma", "tc"])
 @pytest.mark.parametrize("shape", [(2, 6400, 1), (2, 1600, 2), (1, 400, 5), (1, 100, 8), (1, 77, 2), (1, 1000, 1)])
 def test_attention(shape, engine):
     from perspectivefields_b200 import _native
@@ -83,7 +83,8 @@ def test_attention(shape, engine):
     g = torch.Generator().manual_seed(N)
     q, kv = (_rn(g, B, N, C) * 2).cuda(), (_rn(g, B, 100, 2 * C) * 2).cuda()
     o = torch.empty_like(q)
-    fn = _native.lib().pf_op_attention if engine == "fp32" else _native.lib().pf_op_attention_mma
+    L = _native.lib()
+    fn = {"fp32": L.pf_op_attention, "mma": L.pf_op_attention_mma, "tc": L.pf_op_attention_tc}[engine]
     _native.check(fn(q.data_ptr(), kv.data_ptr(), o.data_ptr(), B, N, C, heads, U.stream_ptr()))
     qh = q.double().reshape(B, N, heads, 64).permute(0, 2, 1, 3)
     kvh = kv.double().reshape(B, 100, 2, heads, 64).permute(2, 0, 3, 1, 4)
