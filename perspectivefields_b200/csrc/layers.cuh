@@ -299,7 +299,11 @@ __global__ void __launch_bounds__(256, PF_DW3_MINBLOCKS) dwconv3x3_gelu_kernel(c
 // Depthwise 7x7 conv (pad 3) + bias on NHWC -- ConvNeXt block head, convnext.py:28-30,48.  w: [49][C].
 // thread = 4 channels x (2 rows x 8 consecutive pixels): per input row 14 activation loads serve both output rows; 98 weight +
 // 112 activation loads (16 B) for 3136 FMAs, which balances the L1 path against the FMA pipe (one row x 4 pixels was L1-bound 2.4x)
-__global__ void __launch_bounds__(256) dwconv7x7_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C,
+// (two blocks per SM at 128 registers measured no faster: 22.8 vs 22.5 ms per step with 24 B of spills; profiles/r02_notes.md)
+#ifndef PF_DW7_MINBLOCKS
+#define PF_DW7_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(256, PF_DW7_MINBLOCKS) dwconv7x7_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C,
                                                         const float* __restrict__ w, const float* __restrict__ bias) {
   pdl_wait();
   pdl_launch();
