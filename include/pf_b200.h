@@ -112,6 +112,11 @@ int pf_profile_kernels_read(pf_handle h, char* buf, int cap);
  * "stem_tc": the two 7x7 stems as patch gather + TMA GEMM instead of fp32 direct convolution.
  * "phase_conv1": conv_fuse_conv1 composed with the x2 bilinear upsample in front of it (four output phases on the 160x160 grid
  *   + an exact fp32 border-ring kernel); 0 = materialise the upsampled tensor, conv at 320x320.
+ * "pair": GEMM-mode launches with at least one 256 x BN tile per TPC run on CTA pairs (gemm2_tma.cuh, tcgen05.mma.cta_group::2);
+ *   0 = every launch on the single-CTA kernel.
+ * "pdl": programmatic dependent launch of the graph's kernels (a kernel's prologue overlaps its predecessor's tail).
+ * "fork" (default 0): the spatial-reduction branch of a MiT block on a second stream beside the q projection (measured 1 % slower).
+ * "dw_ln" (default 0): ConvNeXt depthwise 7x7 fused with the LayerNorm behind it (measured slower: profiles/r02_notes.md).
  * "decode_only" (default 0; classification heads): the 73 / 180 logits are never written -- the 1x1 prediction
  *   conv, argmax and bin decode (gravity_head.py:243-244 + utils/utils.py:114-130, latitude_head.py:205-208 + utils.py:148-162)
  *   run in one kernel and pred_gravity / pred_latitude receive the decoded fields [n,2,320,320] / [n,1,320,320] (degrees). */

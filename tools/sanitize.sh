@@ -6,7 +6,7 @@ set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 SAN=/usr/local/cuda/bin/compute-sanitizer
-SEL='test_conv3x3_tma_halo or test_conv_gemm_tma_engine or (test_attention and mma) or test_fused_pred_argmax or test_postprocess_op'
+SEL='test_conv3x3_tma_halo or test_conv_gemm_tma_engine or (test_attention and (mma or tc)) or test_fused_pred_argmax or test_postprocess_op'
 for tool in racecheck synccheck; do
   timeout ${SAN_TIMEOUT:-900} $SAN --tool $tool --print-limit 20 --log-file gpurun_out/sanitize_$tool.log \
     python -m pytest tests/test_gpu_ops.py -x -q -m gpu -k "$SEL" > gpurun_out/sanitize_${tool}_pytest.log 2>&1
