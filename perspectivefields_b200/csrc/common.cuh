@@ -93,7 +93,7 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
 
 // exact-erf GELU (nn.GELU default; mix_transformers.py:20, convnext.py:52):  0.5 x (1 + erf(x / sqrt 2)).
 // erf(z) = sign(z) (1 - erfc|z|) with erfc|z| = 2^q(|z|): q = degree-8 polynomial fitted (weighted minimax, float64) to
-// log2 erfc on [0, 4.2] (erfc(4.2) = 3e-9: clamped beyond), evaluated by Horner FMAs + ONE ex2 -- 16 instructions against ~45
+// log2 erfc on [0, 4.2] (erfc(4.2) = 3e-9: clamped beyond), evaluated by Horner FMAs + ONE ex2 -- 14 instructions against ~45
 // (and two MUFU operations) for libm's branch-free erff.  GELU error over all x: 4.4e-7 absolute, 1.1e-7 relative to max(|x|, 1)
 // -- the same as the fp32 rounding of the erff route (both checked against scipy in float64; tests/test_host_logic.py repeats
 // the check on the coefficients below).  PF_GELU_LIBM selects erff.
@@ -110,10 +110,10 @@ __device__ __forceinline__ float gelu_erf(float x) {
   q = fmaf(q, z, -0.14857476949691772f);
   q = fmaf(q, z, -0.9183977246284485f);
   q = fmaf(q, z, -1.6279100179672241f);
-  q = fmaf(q, z, 2.8043370292607506e-08f);
-  float ec;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ec) : "f"(q));      // erfc(|x| / sqrt 2)
-  return 0.5f * x * (1.0f + copysignf(1.0f - ec, x));
+  q = fmaf(q, z, -0.99999997195662971f);                        // (2.8043370292607506e-08 - 1): ex2 below returns erfc / 2
+  float h;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(h) : "f"(q));       // erfc(|x| / sqrt 2) / 2
+  return fmaf(x, 0.5f, fabsf(x) * (0.5f - h));                  // x/2 + |x| erf(|x| / sqrt 2) / 2
 #endif
 }
 

@@ -237,34 +237,45 @@ inline cudaError_t attention_launch(const float* q, const float* kv, float* out,
 #ifndef PF_DW3_MINBLOCKS
 #define PF_DW3_MINBLOCKS 2     // (3 blocks per SM = 80 registers with spills measured 4 % slower, A/B in profiles/r02_notes.md)
 #endif
+// Index arithmetic is 32-bit in units of float4 (4 channels): o00 = pixel (y0, x0) of the thread's tile, neighbours at +- W*C/4 and
+// +- C/4 (modular unsigned arithmetic: an index is only dereferenced when its row / column predicate holds).  The 64-bit
+// per-load address chains of the first version were a third of the executed instructions (ncu: profiles/r02_notes.md).
 __global__ void __launch_bounds__(256, PF_DW3_MINBLOCKS) dwconv3x3_gelu_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C,
                                                              const float* __restrict__ w, const float* __restrict__ bias,
                                                              __nv_bfloat16* __restrict__ shi = nullptr, __nv_bfloat16* __restrict__ slo = nullptr) {
   pdl_wait();
   pdl_launch();
   // thread = 4 channels x (2 rows x 4 consecutive pixels): 24 activation + 9 weight loads (float4) for 8 outputs
-  const int C4 = C >> 2, XG = (W + 3) >> 2, YG = (H + 1) >> 1;
-  const unsigned total = (unsigned)B * YG * XG * C4;      // < 2^31 for every layer of the network: 32-bit index math
+  const unsigned C4 = (unsigned)C >> 2, XG = ((unsigned)W + 3) >> 2, YG = ((unsigned)H + 1) >> 1;
+  const unsigned total = (unsigned)B * YG * XG * C4;      // < 2^31 for every layer of the network (checked by the host): 32-bit index math
+  const unsigned rs = (unsigned)W * C4;                   // row stride in float4
+  const float4* __restrict__ in4 = reinterpret_cast<const float4*>(in);
+  const float4* __restrict__ w4 = reinterpret_cast<const float4*>(w);
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int c4 = (int)(i % (unsigned)C4);
-    unsigned r = i / (unsigned)C4;
-    const int xg = (int)(r % (unsigned)XG); r /= (unsigned)XG;
-    const int y0 = (int)(r % (unsigned)YG) * 2; const int b = (int)(r / (unsigned)YG);
-    const int x0 = xg * 4;
+    const unsigned c4 = i % C4;
+    unsigned r = i / C4;
+    const unsigned xg = r % XG; r /= XG;
+    const int y0 = (int)(r % YG) * 2; const unsigned b = r / YG;
+    const int x0 = (int)xg * 4;
+    const unsigned o00 = ((b * (unsigned)H + (unsigned)y0) * (unsigned)W + (unsigned)x0) * C4 + c4;
+    bool cv[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) cv[j] = (unsigned)(x0 - 1 + j) < (unsigned)W;
     const float4 bv = __ldg(reinterpret_cast<const float4*>(bias) + c4);
     float4 acc[2][4] = {{bv, bv, bv, bv}, {bv, bv, bv, bv}};
     float4 k[9];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) k[t] = __ldg(reinterpret_cast<const float4*>(w + t * C) + c4);
+    for (int t = 0; t < 9; ++t) k[t] = __ldg(w4 + ((unsigned)t * C4 + c4));
 #pragma unroll
     for (int ry = 0; ry < 4; ++ry) {          // input rows y0-1 .. y0+2
       const int iy = y0 + ry - 1;
       if ((unsigned)iy >= (unsigned)H) continue;
+      const unsigned rb = o00 + (unsigned)(ry - 1) * rs - C4;     // (iy, x0 - 1)
       float4 a[6];
 #pragma unroll
       for (int j = 0; j < 6; ++j) {
-        const int ix = x0 - 1 + j;
-        a[j] = (unsigned)ix < (unsigned)W ? __ldg(reinterpret_cast<const float4*>(in + ((long long)(b * H + iy) * W + ix) * C) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        a[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cv[j]) a[j] = __ldg(in4 + (rb + (unsigned)j * C4));
       }
 #pragma unroll
       for (int oy = 0; oy < 2; ++oy) {        // this input row is filter row ky = ry - oy of output row y0 + oy
@@ -286,11 +297,17 @@ __global__ void __launch_bounds__(256, PF_DW3_MINBLOCKS) dwconv3x3_gelu_kernel(c
       if (y0 + oy >= H) break;
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
-        if (x0 + p >= W) break;
+        if (!cv[p + 1]) break;                 // x0 + p < W
         const float4 o = make_float4(gelu_erf(acc[oy][p].x), gelu_erf(acc[oy][p].y), gelu_erf(acc[oy][p].z), gelu_erf(acc[oy][p].w));
-        const long long oi = ((long long)(b * H + y0 + oy) * W + x0 + p) * C + c4 * 4;
-        if (out) *reinterpret_cast<float4*>(out + oi) = o;
-        if (shi) store_split4(shi, slo, oi, o);
+        const unsigned oi = o00 + (unsigned)oy * rs + (unsigned)p * C4;
+        if (out) reinterpret_cast<float4*>(out)[oi] = o;
+        if (shi) {
+          uint2 h, l;
+          split_bf16x2(o.x, o.y, h.x, l.x);
+          split_bf16x2(o.z, o.w, h.y, l.y);
+          reinterpret_cast<uint2*>(shi)[oi] = h;
+          reinterpret_cast<uint2*>(slo)[oi] = l;
+        }
       }
     }
   }
@@ -307,14 +324,21 @@ __global__ void __launch_bounds__(256, PF_DW7_MINBLOCKS) dwconv7x7_kernel(const 
                                                         const float* __restrict__ w, const float* __restrict__ bias) {
   pdl_wait();
   pdl_launch();
-  const int C4 = C >> 2, XG = (W + 7) >> 3, YG = (H + 1) >> 1;
+  const unsigned C4 = (unsigned)C >> 2, XG = ((unsigned)W + 7) >> 3, YG = ((unsigned)H + 1) >> 1;
   const unsigned total = (unsigned)B * YG * XG * C4;
+  const unsigned rs = (unsigned)W * C4;                   // row stride in float4 (32-bit index arithmetic as dwconv3x3_gelu_kernel)
+  const float4* __restrict__ in4 = reinterpret_cast<const float4*>(in);
+  const float4* __restrict__ w4 = reinterpret_cast<const float4*>(w);
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int c4 = (int)(i % (unsigned)C4);
-    unsigned r = i / (unsigned)C4;
-    const int xg = (int)(r % (unsigned)XG); r /= (unsigned)XG;
-    const int y0 = (int)(r % (unsigned)YG) * 2; const int b = (int)(r / (unsigned)YG);
-    const int x0 = xg * 8;
+    const unsigned c4 = i % C4;
+    unsigned r = i / C4;
+    const unsigned xg = r % XG; r /= XG;
+    const int y0 = (int)(r % YG) * 2; const unsigned b = r / YG;
+    const int x0 = (int)xg * 8;
+    const unsigned o00 = ((b * (unsigned)H + (unsigned)y0) * (unsigned)W + (unsigned)x0) * C4 + c4;
+    bool cv[14];
+#pragma unroll
+    for (int j = 0; j < 14; ++j) cv[j] = (unsigned)(x0 - 3 + j) < (unsigned)W;
     const float4 bv = __ldg(reinterpret_cast<const float4*>(bias) + c4);
     float4 acc[2][8];
 #pragma unroll
@@ -325,11 +349,12 @@ __global__ void __launch_bounds__(256, PF_DW7_MINBLOCKS) dwconv7x7_kernel(const 
     for (int ry = 0; ry < 8; ++ry) {          // input rows y0-3 .. y0+4
       const int iy = y0 + ry - 3;
       if ((unsigned)iy >= (unsigned)H) continue;
+      const unsigned rb = o00 + (unsigned)(ry - 3) * rs - 3u * C4;     // (iy, x0 - 3)
       float4 a[14];
 #pragma unroll
       for (int j = 0; j < 14; ++j) {
-        const int ix = x0 - 3 + j;
-        a[j] = (unsigned)ix < (unsigned)W ? __ldg(reinterpret_cast<const float4*>(in + ((long long)(b * H + iy) * W + ix) * C) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        a[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cv[j]) a[j] = __ldg(in4 + (rb + (unsigned)j * C4));
       }
 #pragma unroll
       for (int oy = 0; oy < 2; ++oy) {        // this input row is filter row ky = ry - oy of output row y0 + oy
@@ -337,7 +362,7 @@ __global__ void __launch_bounds__(256, PF_DW7_MINBLOCKS) dwconv7x7_kernel(const 
         if (ky < 0 || ky > 6) continue;
 #pragma unroll
         for (int kx = 0; kx < 7; ++kx) {
-          const float4 k = __ldg(reinterpret_cast<const float4*>(w + (ky * 7 + kx) * C) + c4);
+          const float4 k = __ldg(w4 + ((unsigned)(ky * 7 + kx) * C4 + c4));
 #pragma unroll
           for (int p = 0; p < 8; ++p) {
             acc[oy][p].x = fmaf(a[p + kx].x, k.x, acc[oy][p].x); acc[oy][p].y = fmaf(a[p + kx].y, k.y, acc[oy][p].y);
@@ -351,8 +376,8 @@ __global__ void __launch_bounds__(256, PF_DW7_MINBLOCKS) dwconv7x7_kernel(const 
       if (y0 + oy >= H) break;
 #pragma unroll
       for (int p = 0; p < 8; ++p) {
-        if (x0 + p >= W) break;
-        *reinterpret_cast<float4*>(out + ((long long)(b * H + y0 + oy) * W + x0 + p) * C + c4 * 4) = acc[oy][p];
+        if (!cv[p + 3]) break;                 // x0 + p < W
+        reinterpret_cast<float4*>(out)[o00 + (unsigned)oy * rs + (unsigned)p * C4] = acc[oy][p];
       }
     }
   }
@@ -477,47 +502,65 @@ inline unsigned ew_grid(long long total) {
 // Bilinear x2 upsample, align_corners=False (decode_head.py:284-286, gravity_head.py:172): taps {0.25, 0.75},
 // edges clamped.  ATen: src = 0.5*(dst+0.5)-0.5 clamped at 0, i1 = min(i0+1, in-1).  NHWC, float4 per thread.
 // `in` channel pitch/offset (ldi, icoff) select one head's half of a 512-channel tensor.
+// thread = 4 channels x (2 output rows x 4 output columns) = the outputs of two neighbouring low-res pixels of one row: 12
+// float4 loads (3 rows x 4 columns, clamped) for 32 results, separable (horizontal, then vertical) -- a third of the loads and
+// half of the instructions of the one-output-pixel-per-thread version.  out[2i] = 0.25 in[i-1] + 0.75 in[i], out[2i+1] =
+// 0.75 in[i] + 0.25 in[i+1]; at the clamped edges both taps are the same pixel and fmaf(0.75, a, 0.25 a) returns a exactly.
+// Index arithmetic is 32-bit in float4 units.
+inline long long upsample2x_threads(int B, int H, int W, int C) { return (long long)B * H * ((W + 1) / 2) * (C / 4); }
 __global__ void __launch_bounds__(256) upsample2x_kernel(const float* __restrict__ in, int ldi, int icoff, float* __restrict__ out, int ldo, int ocoff,
                                                          int B, int H, int W, int C, __nv_bfloat16* __restrict__ shi = nullptr, __nv_bfloat16* __restrict__ slo = nullptr) {
   pdl_wait();
   pdl_launch();
-  // thread = 8 channels of one output pixel (16 B stores to each bf16 plane)
-  const int C8 = C >> 3, OH = 2 * H, OW = 2 * W;
-  const unsigned total = (unsigned)B * OH * OW * C8;     // <= 2^29 for the network's largest tensor at batch 32
+  const unsigned C4 = (unsigned)C >> 2, JG = ((unsigned)W + 1) >> 1, li4 = (unsigned)ldi >> 2, lo4 = (unsigned)ldo >> 2;
+  const unsigned total = (unsigned)B * H * JG * C4;
+  const unsigned OW = 2u * W;
+  const float4* __restrict__ in4 = reinterpret_cast<const float4*>(in + icoff);
+  const unsigned oc4 = (unsigned)ocoff >> 2;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % (unsigned)C8);
-    unsigned pix = i / (unsigned)C8;
-    const int x = (int)(pix % (unsigned)OW); pix /= (unsigned)OW;
-    const int y = (int)(pix % (unsigned)OH); const int b = (int)(pix / (unsigned)OH);
-    const float sy = fmaxf(0.5f * (y + 0.5f) - 0.5f, 0.f), sx = fmaxf(0.5f * (x + 0.5f) - 0.5f, 0.f);
-    const int y0 = (int)sy, x0 = (int)sx;
-    const int y1 = y0 + (y0 < H - 1), x1 = x0 + (x0 < W - 1);
-    const float ly = sy - y0, lx = sx - x0, hy = 1.f - ly, hx = 1.f - lx;
-    const float* base = in + (long long)b * H * W * ldi + icoff + c8 * 8;
-    const long long oi = ((long long)(b * OH + y) * OW + x) * ldo + ocoff + c8 * 8;
-    float4 r[2];
+    const unsigned c4 = i % C4;
+    unsigned r = i / C4;
+    const unsigned jg = r % JG; r /= JG;
+    const int iy = (int)(r % (unsigned)H); const unsigned b = r / (unsigned)H;
+    const int j0 = (int)jg * 2;
+    const bool two = j0 + 1 < W;                                       // second low-res column of the pair exists (odd W: not in the last group)
+    const int cx[4] = {j0 > 0 ? j0 - 1 : 0, j0, j0 + 1 < W ? j0 + 1 : W - 1, j0 + 2 < W ? j0 + 2 : W - 1};
+    const int cy[3] = {iy > 0 ? iy - 1 : 0, iy, iy + 1 < H ? iy + 1 : H - 1};
+    float4 t[3][4];
 #pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
-      const float4 v00 = __ldg(reinterpret_cast<const float4*>(base + (long long)(y0 * W + x0) * ldi + hf * 4));
-      const float4 v01 = __ldg(reinterpret_cast<const float4*>(base + (long long)(y0 * W + x1) * ldi + hf * 4));
-      const float4 v10 = __ldg(reinterpret_cast<const float4*>(base + (long long)(y1 * W + x0) * ldi + hf * 4));
-      const float4 v11 = __ldg(reinterpret_cast<const float4*>(base + (long long)(y1 * W + x1) * ldi + hf * 4));
-      r[hf].x = hy * (hx * v00.x + lx * v01.x) + ly * (hx * v10.x + lx * v11.x);
-      r[hf].y = hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y);
-      r[hf].z = hy * (hx * v00.z + lx * v01.z) + ly * (hx * v10.z + lx * v11.z);
-      r[hf].w = hy * (hx * v00.w + lx * v01.w) + ly * (hx * v10.w + lx * v11.w);
+    for (int ry = 0; ry < 3; ++ry) {
+      const unsigned rb = ((b * (unsigned)H + (unsigned)cy[ry]) * (unsigned)W) * li4 + c4;
+      float4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = __ldg(in4 + (rb + (unsigned)cx[k] * li4));
+#define PF_UP_LERP(d, lo_, hi_)                                                                                 \
+  d.x = fmaf(0.75f, hi_.x, 0.25f * lo_.x); d.y = fmaf(0.75f, hi_.y, 0.25f * lo_.y);                             \
+  d.z = fmaf(0.75f, hi_.z, 0.25f * lo_.z); d.w = fmaf(0.75f, hi_.w, 0.25f * lo_.w);
+      PF_UP_LERP(t[ry][0], v[0], v[1])        // output column 2 j0     : 0.25 in[j0-1] + 0.75 in[j0]
+      PF_UP_LERP(t[ry][1], v[2], v[1])        //               2 j0 + 1 : 0.75 in[j0]   + 0.25 in[j0+1]
+      PF_UP_LERP(t[ry][2], v[1], v[2])        //               2 j0 + 2 : 0.25 in[j0]   + 0.75 in[j0+1]
+      PF_UP_LERP(t[ry][3], v[3], v[2])        //               2 j0 + 3 : 0.75 in[j0+1] + 0.25 in[j0+2]
     }
-    if (out) {
-      *reinterpret_cast<float4*>(out + oi) = r[0];
-      *reinterpret_cast<float4*>(out + oi + 4) = r[1];
+    const unsigned ob = ((b * 2u * (unsigned)H + 2u * (unsigned)iy) * OW + 4u * jg) * lo4 + oc4 + c4;     // output pixel (2 iy, 4 jg)
+#pragma unroll
+    for (int oy = 0; oy < 2; ++oy) {
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        if (p >= 2 && !two) break;
+        float4 o;
+        if (oy == 0) { PF_UP_LERP(o, t[0][p], t[1][p]) } else { PF_UP_LERP(o, t[2][p], t[1][p]) }
+        const unsigned oi = ob + ((unsigned)oy * OW + (unsigned)p) * lo4;
+        if (out) reinterpret_cast<float4*>(out)[oi] = o;
+        if (shi) {
+          uint2 h, l;
+          split_bf16x2(o.x, o.y, h.x, l.x);
+          split_bf16x2(o.z, o.w, h.y, l.y);
+          reinterpret_cast<uint2*>(shi)[oi] = h;
+          reinterpret_cast<uint2*>(slo)[oi] = l;
+        }
+      }
     }
-    if (shi) {
-      uint4 h, l;
-      split_bf16x2(r[0].x, r[0].y, h.x, l.x); split_bf16x2(r[0].z, r[0].w, h.y, l.y);
-      split_bf16x2(r[1].x, r[1].y, h.z, l.z); split_bf16x2(r[1].z, r[1].w, h.w, l.w);
-      *reinterpret_cast<uint4*>(shi + oi) = h;
-      *reinterpret_cast<uint4*>(slo + oi) = l;
-    }
+#undef PF_UP_LERP
   }
 }
 

@@ -882,12 +882,12 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
       { Epi o; o.C = w2; o.ldc = 512; o.res = of; o.ldr = 512; o.res_relu = 1; TRY(rcu(u, e->rcu[lvl - 1][1][1], o)); }
       if (lvl > 1) {
         float* up = ar.f(px * 4 * 512);
-        if (!dry) LAUNCHED(launch_pdl(upsample2x_kernel, dim3(ew_grid(px * 4 * 64)), dim3(256), 0, st, w2, 512, 0, up, 512, 0, n, r, r, 512, nullptr, nullptr));
+        if (!dry) LAUNCHED(launch_pdl(upsample2x_kernel, dim3(ew_grid(upsample2x_threads(n, r, r, 512))), dim3(256), 0, st, w2, 512, 0, up, 512, 0, n, r, r, 512, nullptr, nullptr));
         fused = up;
         TRY(F.tapf(up, px * 4 * 512, "head.fusion%d", lvl));
       } else {
         fused_s = F.salloc(px * 4, 512);
-        if (!dry) LAUNCHED(launch_pdl(upsample2x_kernel, dim3(ew_grid(px * 4 * 64)), dim3(256), 0, st, w2, 512, 0, nullptr, 512, 0, n, r, r, 512, fused_s.hi, fused_s.lo));
+        if (!dry) LAUNCHED(launch_pdl(upsample2x_kernel, dim3(ew_grid(upsample2x_threads(n, r, r, 512))), dim3(256), 0, st, w2, 512, 0, nullptr, 512, 0, n, r, r, 512, fused_s.hi, fused_s.lo));
         TRY(F.tap_split("head.fusion1", fused_s, px * 4 * 512));
       }
     }
@@ -924,7 +924,7 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
         TRY(F.tap("head.conv0", c0, (long long)n * 160 * 160 * 128));
       }
       SplitT c0u = F.salloc((long long)n * kNet * kNet, 128);
-      if (!dry) LAUNCHED(launch_pdl(upsample2x_kernel, dim3(ew_grid((long long)n * kNet * kNet * 16)), dim3(256), 0, st, c0, 128, 0, nullptr, 128, 0, n, 160, 160, 128, c0u.hi, c0u.lo));
+      if (!dry) LAUNCHED(launch_pdl(upsample2x_kernel, dim3(ew_grid(upsample2x_threads(n, 160, 160, 128))), dim3(256), 0, st, c0, 128, 0, nullptr, 128, 0, n, 160, 160, 128, c0u.hi, c0u.lo));
       Epi o; o.ldc = 64; o.c_gcoff = 32; o.act = 1;
       if (keep_conv1) o.C = conv1_out;
       TRY(F.thalo(c0u, 0, 64, nullptr, 0, 0, n, kNet, kNet, 64, e->conv1, 32, 2, 32, o, fuse_pred ? pt : nullptr));
@@ -1576,8 +1576,8 @@ int pf_op_dwconv7x7(const float* x, float* y, int B, int H, int W, int C, const 
   return PF_OK;
 }
 int pf_op_upsample2x(const float* x, float* y, int B, int H, int W, int C, void* stream) {
-  if (C % 8) return fail(PF_ERR_ARG, "C %% 8");
-  LAUNCHED(launch_pdl(upsample2x_kernel, dim3(ew_grid((long long)B * H * W * C / 2)), dim3(256), 0, (cudaStream_t)stream, x, C, 0, y, C, 0, B, H, W, C, nullptr, nullptr));
+  if (C % 4) return fail(PF_ERR_ARG, "C %% 4");
+  LAUNCHED(launch_pdl(upsample2x_kernel, dim3(ew_grid(upsample2x_threads(B, H, W, C))), dim3(256), 0, (cudaStream_t)stream, x, C, 0, y, C, 0, B, H, W, C, nullptr, nullptr));
   return PF_OK;
 }
 int pf_op_preprocess(const uint8_t* img, int H, int W, const float* mean3, const float* std3, float* y, void* stream) {

@@ -122,8 +122,10 @@ def test_gelu_polynomial_in_the_kernels_matches_erf():
     q = np.full_like(z, f32(lead))
     for c in rest:
         q = q * z + f32(c)
-    ec = np.exp2(q).astype(f32)
-    g = (f32(0.5) * x * (f32(1) + np.copysign(f32(1) - ec, x))).astype(np.float64)
+    assert abs(rest[-1] + 1.0) < 1e-7                     # the constant term carries the 1/2: ex2 returns erfc / 2
+    h = np.exp2(q).astype(f32)
+    t = (np.abs(x) * (f32(0.5) - h)).astype(f32)
+    g = (x.astype(np.float64) * 0.5 + t.astype(np.float64)).astype(f32).astype(np.float64)     # fmaf(x, 0.5, t): one rounding
     xd = x.astype(np.float64)
     exact = 0.5 * xd * (1 + erf(xd / math.sqrt(2)))
     err = np.abs(g - exact)
