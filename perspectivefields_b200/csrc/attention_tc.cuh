@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(kAtcThreads, 1) attention_tc_kernel(const __gr
       float l = 0.f;
 #pragma unroll
       for (int k = 0; k < kAtcKeysPad; ++k) {
-        p[k] = k < kAtcKeys ? exp2f(fmaf(p[k], kScale, -mc)) : 0.f;
+        p[k] = k < kAtcKeys ? ex2_approx(fmaf(p[k], kScale, -mc)) : 0.f;
         l += p[k];
       }
       // P -> shared memory (A operand of the second contraction), once the MMAs of the previous item have consumed the buffer

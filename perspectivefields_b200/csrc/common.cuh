@@ -117,6 +117,13 @@ __device__ __forceinline__ float gelu_erf(float x) {
 #endif
 }
 
+// 2^x on the special-function unit (2 ulp; results below 2^-126 flush to zero -- softmax weights that small do not matter)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

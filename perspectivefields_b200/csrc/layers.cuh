@@ -78,75 +78,108 @@ inline cudaError_t stem_conv_launch(const float* in, int ldin, int B, int H, int
 // LayerNorm over the channel dimension of [rows, C] (nn.LayerNorm / F.layer_norm, biased variance, eps inside
 // the sqrt) -- mix_transformers.py:199-200,247,120,457 and convnext.py:172-182 (both data formats reduce to this
 // in NHWC).  One warp per row; two-pass (mean, then centred variance) in registers.
-template <int MAXQ, int LANES>   // float4 quads per lane; LANES (32 or 16) lanes cooperate on one row: lane owns quads lane + LANES*i
-__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ in, float* __restrict__ out, long long rows, int C,
+// NR independent rows per lane group are in flight at once (all their loads are issued before the first reduction): with one row
+// per warp the kernel was bound by the latency of that single load, not by bandwidth.  Index arithmetic is 32-bit in float4 units
+// (rows * C / 4 < 2^32, checked by the launcher).
+template <int MAXQ, int LANES, int NR>   // float4 quads per lane; LANES (32 or 16) lanes cooperate on one row: lane owns quads lane + LANES*i
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ in, float* __restrict__ out, long long rows_ll, int C,
                                                         const float* __restrict__ gw, const float* __restrict__ gb, float eps,
                                                         __nv_bfloat16* __restrict__ shi, __nv_bfloat16* __restrict__ slo,
                                                         __nv_bfloat16* __restrict__ phi, __nv_bfloat16* __restrict__ plo, int R, int sr) {
   pdl_wait();
   pdl_launch();
-  constexpr int RPW = 32 / LANES;       // rows per warp
-  const int lane = threadIdx.x & (LANES - 1);
-  const long long row = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + ((threadIdx.x & 31) / LANES);
-  const bool ok = row < rows;
-  const int Q = C >> 2;
-  const float4* x = reinterpret_cast<const float4*>(in + (ok ? row : 0) * C);
-  float4 v[MAXQ];
-  float s = 0.f;
+  constexpr int RPW = 32 / LANES;       // lane groups (rows) per warp
+  const unsigned lane = threadIdx.x & (LANES - 1);
+  const unsigned rows = (unsigned)rows_ll;
+  const unsigned row0 = ((blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + ((threadIdx.x & 31) / LANES)) * NR;
+  const unsigned Q = (unsigned)C >> 2;
+  const float inv_c = 1.0f / (float)C;
+  const float4* __restrict__ in4 = reinterpret_cast<const float4*>(in);
+  float4 v[NR][MAXQ];
+  float s[NR], q[NR];
 #pragma unroll
-  for (int i = 0; i < MAXQ; ++i) {
-    const int qd = lane + LANES * i;
-    v[i] = (ok && qd < Q) ? x[qd] : make_float4(0.f, 0.f, 0.f, 0.f);
-    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-  }
+  for (int j = 0; j < NR; ++j) {
+    const bool ok = row0 + j < rows;
+    const unsigned xb = (ok ? row0 + j : 0u) * Q;
+    s[j] = 0.f;
 #pragma unroll
-  for (int o = LANES / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / (float)C;
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < MAXQ; ++i) {
-    if (lane + LANES * i < Q) {
-      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-      q = fmaf(a, a, q); q = fmaf(b, b, q); q = fmaf(c, c, q); q = fmaf(d, d, q);
+    for (int i = 0; i < MAXQ; ++i) {
+      const unsigned qd = lane + LANES * i;
+      v[j][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok && qd < Q) v[j][i] = __ldg(in4 + (xb + qd));
+      s[j] += (v[j][i].x + v[j][i].y) + (v[j][i].z + v[j][i].w);
     }
   }
 #pragma unroll
-  for (int o = LANES / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float rstd = 1.0f / sqrtf(q / (float)C + eps);
-  if (!ok) return;
+  for (int o = LANES / 2; o > 0; o >>= 1)
+#pragma unroll
+    for (int j = 0; j < NR; ++j) s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+#pragma unroll
+  for (int j = 0; j < NR; ++j) {
+    s[j] *= inv_c;                      // mean
+    q[j] = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXQ; ++i) {
+      if (lane + LANES * i < Q) {
+        const float a = v[j][i].x - s[j], b = v[j][i].y - s[j], c = v[j][i].z - s[j], d = v[j][i].w - s[j];
+        q[j] = fmaf(a, a, q[j]); q[j] = fmaf(b, b, q[j]); q[j] = fmaf(c, c, q[j]); q[j] = fmaf(d, d, q[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = LANES / 2; o > 0; o >>= 1)
+#pragma unroll
+    for (int j = 0; j < NR; ++j) q[j] += __shfl_xor_sync(0xffffffffu, q[j], o);
   // optional second copy in PATCH order for a k = s = sr convolution that follows (spatial-reduction conv of the attention,
   // mix_transformers.py:112-117; ConvNeXt downsample 2x2/2, convnext.py:93-99): token (b, y, x) of an R x R map goes to row
   // (b, y / sr, x / sr), columns ((y % sr) * sr + x % sr) * C + c -- the im2col matrix of that convolution, written by the
   // producer instead of a separate gather kernel
-  long long prow = 0;
-  if (phi) {
-    const int x = (int)(row % R), y = (int)((row / R) % R);
-    const long long b = row / ((long long)R * R);
-    const int OR = R / sr;
-    prow = (((b * OR + y / sr) * OR + x / sr) * (sr * sr) + (y % sr) * sr + x % sr) * C;
-  }
 #pragma unroll
-  for (int i = 0; i < MAXQ; ++i) {
-    const int qd = lane + LANES * i;
-    if (qd < Q) {
-      const float4 w = __ldg(reinterpret_cast<const float4*>(gw) + qd), b = __ldg(reinterpret_cast<const float4*>(gb) + qd);
-      const float4 y = make_float4((v[i].x - mean) * rstd * w.x + b.x, (v[i].y - mean) * rstd * w.y + b.y,
-                                   (v[i].z - mean) * rstd * w.z + b.z, (v[i].w - mean) * rstd * w.w + b.w);
-      if (out) reinterpret_cast<float4*>(out + row * C)[qd] = y;
-      if (shi) store_split4(shi, slo, row * C + qd * 4, y);
-      if (phi) store_split4(phi, plo, prow + qd * 4, y);
+  for (int j = 0; j < NR; ++j) {
+    const unsigned row = row0 + j;
+    if (row >= rows) break;
+    const float mean = s[j];
+    const float rstd = 1.0f / sqrtf(fmaf(q[j], inv_c, eps));
+    unsigned pb = 0;
+    if (phi) {
+      const unsigned uR = (unsigned)R, usr = (unsigned)sr;
+      const unsigned x = row % uR, t = row / uR, y = t % uR, b = t / uR;
+      const unsigned OR = uR / usr;
+      pb = (((b * OR + y / usr) * OR + x / usr) * (usr * usr) + (y % usr) * usr + x % usr) * Q;
+    }
+    const unsigned ob = row * Q;
+#pragma unroll
+    for (int i = 0; i < MAXQ; ++i) {
+      const unsigned qd = lane + LANES * i;
+      if (qd < Q) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(gw) + qd), b = __ldg(reinterpret_cast<const float4*>(gb) + qd);
+        const float4 y = make_float4((v[j][i].x - mean) * rstd * w.x + b.x, (v[j][i].y - mean) * rstd * w.y + b.y,
+                                     (v[j][i].z - mean) * rstd * w.z + b.z, (v[j][i].w - mean) * rstd * w.w + b.w);
+        if (out) reinterpret_cast<float4*>(out)[ob + qd] = y;
+        if (shi || phi) {
+          uint2 h, l;
+          split_bf16x2(y.x, y.y, h.x, l.x);
+          split_bf16x2(y.z, y.w, h.y, l.y);
+          if (shi) { reinterpret_cast<uint2*>(shi)[ob + qd] = h; reinterpret_cast<uint2*>(slo)[ob + qd] = l; }
+          if (phi) { reinterpret_cast<uint2*>(phi)[pb + qd] = h; reinterpret_cast<uint2*>(plo)[pb + qd] = l; }
+        }
+      }
     }
   }
 }
 
+#ifndef PF_LN_NR3
+#define PF_LN_NR3 1            // rows in flight per lane group for C > 128 (A/B: 1 row 1.58 ms, 2 rows 1.64 ms, 4 rows 1.65 ms per step; C <= 128: 4 rows)
+#endif
 inline cudaError_t layernorm_launch(const float* in, float* out, long long rows, int C, const float* w, const float* b, float eps,
                                     cudaStream_t st, SplitT sp = SplitT(), SplitT patch = SplitT(), int R = 0, int sr = 0) {
-  if (C % 4 || C > 768) return cudaErrorInvalidValue;
+  if (C % 4 || C > 768 || rows * (C / 4) >= (1LL << 32)) return cudaErrorInvalidValue;
   if (patch.hi && (R < 1 || sr < 1 || R % sr || rows % ((long long)R * R))) return cudaErrorInvalidValue;
-  if (C <= 64) return launch_pdl(layernorm_kernel<1, 16>, dim3((unsigned)cdivl(rows, 16)), dim3(256), 0, st, in, out, rows, C, w, b, eps, sp.hi, sp.lo, patch.hi, patch.lo, R, sr);   // two rows per warp
-  if (C <= 128) return launch_pdl(layernorm_kernel<1, 32>, dim3((unsigned)cdivl(rows, 8)), dim3(256), 0, st, in, out, rows, C, w, b, eps, sp.hi, sp.lo, patch.hi, patch.lo, R, sr);
-  if (C <= 384) return launch_pdl(layernorm_kernel<3, 32>, dim3((unsigned)cdivl(rows, 8)), dim3(256), 0, st, in, out, rows, C, w, b, eps, sp.hi, sp.lo, patch.hi, patch.lo, R, sr);
-  return launch_pdl(layernorm_kernel<6, 32>, dim3((unsigned)cdivl(rows, 8)), dim3(256), 0, st, in, out, rows, C, w, b, eps, sp.hi, sp.lo, patch.hi, patch.lo, R, sr);
+  // rows per block = 8 warps x (32 / LANES) lane groups x NR rows in flight per group
+  if (C <= 64) return launch_pdl(layernorm_kernel<1, 16, 4>, dim3((unsigned)cdivl(rows, 64)), dim3(256), 0, st, in, out, rows, C, w, b, eps, sp.hi, sp.lo, patch.hi, patch.lo, R, sr);
+  if (C <= 128) return launch_pdl(layernorm_kernel<1, 32, 4>, dim3((unsigned)cdivl(rows, 32)), dim3(256), 0, st, in, out, rows, C, w, b, eps, sp.hi, sp.lo, patch.hi, patch.lo, R, sr);
+  if (C <= 384) return launch_pdl(layernorm_kernel<3, 32, PF_LN_NR3>, dim3((unsigned)cdivl(rows, 8 * PF_LN_NR3)), dim3(256), 0, st, in, out, rows, C, w, b, eps, sp.hi, sp.lo, patch.hi, patch.lo, R, sr);
+  return launch_pdl(layernorm_kernel<6, 32, PF_LN_NR3>, dim3((unsigned)cdivl(rows, 8 * PF_LN_NR3)), dim3(256), 0, st, in, out, rows, C, w, b, eps, sp.hi, sp.lo, patch.hi, patch.lo, R, sr);
 }
 
 // =====================================================================================================
@@ -234,6 +267,12 @@ inline cudaError_t attention_launch(const float* q, const float* kv, float* out,
 // =====================================================================================================
 // Depthwise 3x3 conv (pad 1) + bias + GELU(erf) on NHWC -- Mix-FFN middle, mix_transformers.py:51-52,502-508.
 // w: [9][C], thread = 4 channels of one pixel.
+#ifndef PF_DW3_PX
+#define PF_DW3_PX 4            // output pixels per thread along x (x 2 rows x 4 channels)
+#endif
+#ifndef PF_DW3_HOIST
+#define PF_DW3_HOIST 1          // A/B on one box: 1.40 ms per step hoisted, 1.455 ms row by row
+#endif
 #ifndef PF_DW3_MINBLOCKS
 #define PF_DW3_MINBLOCKS 2     // (3 blocks per SM = 80 registers with spills measured 4 % slower, A/B in profiles/r02_notes.md)
 #endif
@@ -245,8 +284,9 @@ __global__ void __launch_bounds__(256, PF_DW3_MINBLOCKS) dwconv3x3_gelu_kernel(c
                                                              __nv_bfloat16* __restrict__ shi = nullptr, __nv_bfloat16* __restrict__ slo = nullptr) {
   pdl_wait();
   pdl_launch();
-  // thread = 4 channels x (2 rows x 4 consecutive pixels): 24 activation + 9 weight loads (float4) for 8 outputs
-  const unsigned C4 = (unsigned)C >> 2, XG = ((unsigned)W + 3) >> 2, YG = ((unsigned)H + 1) >> 1;
+  // thread = 4 channels x (2 rows x PX consecutive pixels): 4 (PX + 2) activation + 9 weight loads (float4) for 2 PX outputs
+  constexpr int PX = PF_DW3_PX;
+  const unsigned C4 = (unsigned)C >> 2, XG = ((unsigned)W + PX - 1) / PX, YG = ((unsigned)H + 1) >> 1;
   const unsigned total = (unsigned)B * YG * XG * C4;      // < 2^31 for every layer of the network (checked by the host): 32-bit index math
   const unsigned rs = (unsigned)W * C4;                   // row stride in float4
   const float4* __restrict__ in4 = reinterpret_cast<const float4*>(in);
@@ -256,24 +296,58 @@ __global__ void __launch_bounds__(256, PF_DW3_MINBLOCKS) dwconv3x3_gelu_kernel(c
     unsigned r = i / C4;
     const unsigned xg = r % XG; r /= XG;
     const int y0 = (int)(r % YG) * 2; const unsigned b = r / YG;
-    const int x0 = (int)xg * 4;
+    const int x0 = (int)xg * PX;
     const unsigned o00 = ((b * (unsigned)H + (unsigned)y0) * (unsigned)W + (unsigned)x0) * C4 + c4;
-    bool cv[6];
+    bool cv[PX + 2];
 #pragma unroll
-    for (int j = 0; j < 6; ++j) cv[j] = (unsigned)(x0 - 1 + j) < (unsigned)W;
+    for (int j = 0; j < PX + 2; ++j) cv[j] = (unsigned)(x0 - 1 + j) < (unsigned)W;
     const float4 bv = __ldg(reinterpret_cast<const float4*>(bias) + c4);
-    float4 acc[2][4] = {{bv, bv, bv, bv}, {bv, bv, bv, bv}};
+    float4 acc[2][PX];
+#pragma unroll
+    for (int p = 0; p < PX; ++p) acc[0][p] = acc[1][p] = bv;
     float4 k[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) k[t] = __ldg(w4 + ((unsigned)t * C4 + c4));
+#if PF_DW3_HOIST
+    // all 4 (PX + 2) loads are issued before the first FMA (rows outside the image contribute zeros): one exposed memory latency
+    // per tile instead of one per input row
+    float4 a[4][PX + 2];
+#pragma unroll
+    for (int ry = 0; ry < 4; ++ry) {
+      const bool rv = (unsigned)(y0 + ry - 1) < (unsigned)H;
+      const unsigned rb = o00 + (unsigned)(ry - 1) * rs - C4;     // (iy, x0 - 1)
+#pragma unroll
+      for (int j = 0; j < PX + 2; ++j) {
+        a[ry][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rv && cv[j]) a[ry][j] = __ldg(in4 + (rb + (unsigned)j * C4));
+      }
+    }
+#pragma unroll
+    for (int ry = 0; ry < 4; ++ry) {
+#pragma unroll
+      for (int oy = 0; oy < 2; ++oy) {
+        const int ky = ry - oy;
+        if (ky < 0 || ky > 2) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const float4 kk = k[ky * 3 + kx];
+#pragma unroll
+          for (int p = 0; p < PX; ++p) {
+            acc[oy][p].x = fmaf(a[ry][p + kx].x, kk.x, acc[oy][p].x); acc[oy][p].y = fmaf(a[ry][p + kx].y, kk.y, acc[oy][p].y);
+            acc[oy][p].z = fmaf(a[ry][p + kx].z, kk.z, acc[oy][p].z); acc[oy][p].w = fmaf(a[ry][p + kx].w, kk.w, acc[oy][p].w);
+          }
+        }
+      }
+    }
+#else
 #pragma unroll
     for (int ry = 0; ry < 4; ++ry) {          // input rows y0-1 .. y0+2
       const int iy = y0 + ry - 1;
       if ((unsigned)iy >= (unsigned)H) continue;
       const unsigned rb = o00 + (unsigned)(ry - 1) * rs - C4;     // (iy, x0 - 1)
-      float4 a[6];
+      float4 a[PX + 2];
 #pragma unroll
-      for (int j = 0; j < 6; ++j) {
+      for (int j = 0; j < PX + 2; ++j) {
         a[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (cv[j]) a[j] = __ldg(in4 + (rb + (unsigned)j * C4));
       }
@@ -285,18 +359,19 @@ __global__ void __launch_bounds__(256, PF_DW3_MINBLOCKS) dwconv3x3_gelu_kernel(c
         for (int kx = 0; kx < 3; ++kx) {
           const float4 kk = k[ky * 3 + kx];
 #pragma unroll
-          for (int p = 0; p < 4; ++p) {
+          for (int p = 0; p < PX; ++p) {
             acc[oy][p].x = fmaf(a[p + kx].x, kk.x, acc[oy][p].x); acc[oy][p].y = fmaf(a[p + kx].y, kk.y, acc[oy][p].y);
             acc[oy][p].z = fmaf(a[p + kx].z, kk.z, acc[oy][p].z); acc[oy][p].w = fmaf(a[p + kx].w, kk.w, acc[oy][p].w);
           }
         }
       }
     }
+#endif
 #pragma unroll
     for (int oy = 0; oy < 2; ++oy) {
       if (y0 + oy >= H) break;
 #pragma unroll
-      for (int p = 0; p < 4; ++p) {
+      for (int p = 0; p < PX; ++p) {
         if (!cv[p + 1]) break;                 // x0 + p < W
         const float4 o = make_float4(gelu_erf(acc[oy][p].x), gelu_erf(acc[oy][p].y), gelu_erf(acc[oy][p].z), gelu_erf(acc[oy][p].w));
         const unsigned oi = o00 + (unsigned)oy * rs + (unsigned)p * C4;
@@ -317,14 +392,18 @@ __global__ void __launch_bounds__(256, PF_DW3_MINBLOCKS) dwconv3x3_gelu_kernel(c
 // thread = 4 channels x (2 rows x 8 consecutive pixels): per input row 14 activation loads serve both output rows; 98 weight +
 // 112 activation loads (16 B) for 3136 FMAs, which balances the L1 path against the FMA pipe (one row x 4 pixels was L1-bound 2.4x)
 // (two blocks per SM at 128 registers measured no faster: 22.8 vs 22.5 ms per step with 24 B of spills; profiles/r02_notes.md)
+#ifndef PF_DW7_PX
+#define PF_DW7_PX 4            // output pixels per thread along x (x 2 rows x 4 channels); A/B: 4 px at 2 blocks / SM 0.78 ms, 8 px at 1 block 0.84 ms
+#endif
 #ifndef PF_DW7_MINBLOCKS
-#define PF_DW7_MINBLOCKS 1
+#define PF_DW7_MINBLOCKS 2
 #endif
 __global__ void __launch_bounds__(256, PF_DW7_MINBLOCKS) dwconv7x7_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C,
                                                         const float* __restrict__ w, const float* __restrict__ bias) {
   pdl_wait();
   pdl_launch();
-  const unsigned C4 = (unsigned)C >> 2, XG = ((unsigned)W + 7) >> 3, YG = ((unsigned)H + 1) >> 1;
+  constexpr int PX = PF_DW7_PX;
+  const unsigned C4 = (unsigned)C >> 2, XG = ((unsigned)W + PX - 1) / PX, YG = ((unsigned)H + 1) >> 1;
   const unsigned total = (unsigned)B * YG * XG * C4;
   const unsigned rs = (unsigned)W * C4;                   // row stride in float4 (32-bit index arithmetic as dwconv3x3_gelu_kernel)
   const float4* __restrict__ in4 = reinterpret_cast<const float4*>(in);
@@ -334,25 +413,25 @@ __global__ void __launch_bounds__(256, PF_DW7_MINBLOCKS) dwconv7x7_kernel(const 
     unsigned r = i / C4;
     const unsigned xg = r % XG; r /= XG;
     const int y0 = (int)(r % YG) * 2; const unsigned b = r / YG;
-    const int x0 = (int)xg * 8;
+    const int x0 = (int)xg * PX;
     const unsigned o00 = ((b * (unsigned)H + (unsigned)y0) * (unsigned)W + (unsigned)x0) * C4 + c4;
-    bool cv[14];
+    bool cv[PX + 6];
 #pragma unroll
-    for (int j = 0; j < 14; ++j) cv[j] = (unsigned)(x0 - 3 + j) < (unsigned)W;
+    for (int j = 0; j < PX + 6; ++j) cv[j] = (unsigned)(x0 - 3 + j) < (unsigned)W;
     const float4 bv = __ldg(reinterpret_cast<const float4*>(bias) + c4);
-    float4 acc[2][8];
+    float4 acc[2][PX];
 #pragma unroll
     for (int oy = 0; oy < 2; ++oy)
 #pragma unroll
-      for (int p = 0; p < 8; ++p) acc[oy][p] = bv;
+      for (int p = 0; p < PX; ++p) acc[oy][p] = bv;
 #pragma unroll
     for (int ry = 0; ry < 8; ++ry) {          // input rows y0-3 .. y0+4
       const int iy = y0 + ry - 3;
       if ((unsigned)iy >= (unsigned)H) continue;
       const unsigned rb = o00 + (unsigned)(ry - 3) * rs - 3u * C4;     // (iy, x0 - 3)
-      float4 a[14];
+      float4 a[PX + 6];
 #pragma unroll
-      for (int j = 0; j < 14; ++j) {
+      for (int j = 0; j < PX + 6; ++j) {
         a[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (cv[j]) a[j] = __ldg(in4 + (rb + (unsigned)j * C4));
       }
@@ -364,7 +443,7 @@ __global__ void __launch_bounds__(256, PF_DW7_MINBLOCKS) dwconv7x7_kernel(const 
         for (int kx = 0; kx < 7; ++kx) {
           const float4 k = __ldg(w4 + ((unsigned)(ky * 7 + kx) * C4 + c4));
 #pragma unroll
-          for (int p = 0; p < 8; ++p) {
+          for (int p = 0; p < PX; ++p) {
             acc[oy][p].x = fmaf(a[p + kx].x, k.x, acc[oy][p].x); acc[oy][p].y = fmaf(a[p + kx].y, k.y, acc[oy][p].y);
             acc[oy][p].z = fmaf(a[p + kx].z, k.z, acc[oy][p].z); acc[oy][p].w = fmaf(a[p + kx].w, k.w, acc[oy][p].w);
           }
@@ -375,7 +454,7 @@ __global__ void __launch_bounds__(256, PF_DW7_MINBLOCKS) dwconv7x7_kernel(const 
     for (int oy = 0; oy < 2; ++oy) {
       if (y0 + oy >= H) break;
 #pragma unroll
-      for (int p = 0; p < 8; ++p) {
+      for (int p = 0; p < PX; ++p) {
         if (!cv[p + 3]) break;                 // x0 + p < W
         reinterpret_cast<float4*>(out)[o00 + (unsigned)oy * rs + (unsigned)p * C4] = acc[oy][p];
       }
@@ -597,6 +676,9 @@ __global__ void __launch_bounds__(256) im2col_split_kernel(const __nv_bfloat16* 
 // Patch gather for the 7x7 stems (patch_embed1: stride 4, ll_enc: stride 2; pad 3) straight from the normalised input
 // x0 [B,320,320,4] fp32 (b,g,r,0): dst[m][(ky*7+kx)*3 + c] split into bf16 hi/lo, K padded 147 -> 160 with zeros, so that the
 // stems run on the TMA GEMM engine too.  One thread = one output pixel x 8 consecutive K columns (16 B per plane).
+// (A one-pixel-per-thread variant -- 49 float4 loads, 40 16-byte stores into the thread's own 320-byte row -- executed a third of
+// the instructions and ran 3x SLOWER: every store instruction of a warp touched 32 different rows.  profiles/r02_notes.md)
+inline long long stem_gather_threads(int B, int OH, int OW) { return (long long)B * OH * OW * 20; }
 __global__ void __launch_bounds__(256) stem_gather_kernel(const float* __restrict__ x0, __nv_bfloat16* __restrict__ dhi, __nv_bfloat16* __restrict__ dlo,
                                                           int B, int OH, int OW, int stride) {
   pdl_wait();
@@ -607,7 +689,9 @@ __global__ void __launch_bounds__(256) stem_gather_kernel(const float* __restric
     const int kq = (int)(i % KQ);
     unsigned m = i / KQ;
     const int ox = (int)(m % (unsigned)OW); unsigned t = m / (unsigned)OW;
-    const int oy = (int)(t % (unsigned)OH); const int b = (int)(t / (unsigned)OH);
+    const int oy = (int)(t % (unsigned)OH); const unsigned b = t / (unsigned)OH;
+    const int iy0 = oy * stride - 3, ix0 = ox * stride - 3;
+    const unsigned pb = ((b * kNet + (unsigned)iy0) * kNet + (unsigned)ix0) * 4u;     // float index of pixel (iy0, ix0), dereferenced where valid
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -616,8 +700,7 @@ __global__ void __launch_bounds__(256) stem_gather_kernel(const float* __restric
       if (k < 147) {
         const int tap = k / 3, c = k - tap * 3;
         const int ky = tap / 7, kx = tap - ky * 7;
-        const int iy = oy * stride - 3 + ky, ix = ox * stride - 3 + kx;
-        if ((unsigned)iy < (unsigned)kNet && (unsigned)ix < (unsigned)kNet) val = __ldg(x0 + ((long long)(b * kNet + iy) * kNet + ix) * 4 + c);
+        if ((unsigned)(iy0 + ky) < (unsigned)kNet && (unsigned)(ix0 + kx) < (unsigned)kNet) val = __ldg(x0 + (pb + (unsigned)((ky * kNet + kx) * 4 + c)));
       }
       v[e] = val;
     }
@@ -685,7 +768,10 @@ __global__ void __launch_bounds__(128) pred_tail_kernel(const float* __restrict_
 // u = bilinear_x2(c0) sampled on the fly (align_corners=False: src = max(0, (i + 0.5) / 2 - 0.5), neighbour index clamped),
 // zero outside the image, 3x3 taps, + bias, ReLU; then (regression heads) the same fused prediction tail as the GEMM epilogue.
 // c0: split planes [B, H, W, 128] (gravity channels 0-63, latitude 64-127); wf: [2][9][64][32] fp32; out NHWC [B, 2H, 2W, 64].
-// Block = 64 ring pixels x both heads; warp w -> head w / 4, output channels (w % 4) * 8 .. + 8; lane -> pixels lane, lane + 32.
+// Block = 64 ring pixels x both heads; warp w -> head w / 4, pixels (w % 4) * 16 .. + 16; lane = output channel.  Per filter tap the
+// block stages the tap's weights and the upsampled inputs of its pixels (16 lanes read the 128 channels of one source pixel:
+// coalesced 256-byte rows -- with one pixel per lane every 16-byte load pulled its own 32-byte sector and the kernel was bound by
+// L2 sector traffic), then each lane accumulates its channel for 16 pixels from broadcast 16-byte reads of the inputs.
 constexpr int kRingPx = 64;
 __host__ __device__ inline int conv1_ring_count(int H2, int W2) { return 4 * W2 + 4 * (H2 - 4); }
 __global__ void __launch_bounds__(256) conv1_ring_kernel(const __nv_bfloat16* __restrict__ chi, const __nv_bfloat16* __restrict__ clo, int H, int W,
@@ -693,9 +779,8 @@ __global__ void __launch_bounds__(256) conv1_ring_kernel(const __nv_bfloat16* __
                                                          const float* __restrict__ pg_w, const float* __restrict__ pg_b, float* __restrict__ pg_out,
                                                          const float* __restrict__ pl_w, const float* __restrict__ pl_b, float* __restrict__ pl_out) {
   extern __shared__ __align__(16) float s_ring[];
-  float* sU = s_ring;                        // [128 ch][64 px]
+  float* sU = s_ring;                        // [64 px][128 ch]; after the last tap: conv1 outputs [64 px][65] for the prediction tail
   float* sW = s_ring + 128 * kRingPx;        // [2][64 ci][32 o]
-  float* sP = sW + 2 * 64 * 32;              // [64 px][3 outputs][4 channel quarters]
   __shared__ int s_y[kRingPx], s_x[kRingPx];
   const int H2 = 2 * H, W2 = 2 * W, ring = conv1_ring_count(H2, W2);
   const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -706,12 +791,10 @@ __global__ void __launch_bounds__(256) conv1_ring_kernel(const __nv_bfloat16* __
     else if (r < ring) { const int q = r - 4 * W2, k = q & 3; y = 2 + (q >> 2); x = k < 2 ? k : W2 - 4 + k; }
     s_y[tid] = y; s_x[tid] = x;
   }
-  const int g = warp >> 2, oq = warp & 3;
-  float acc[2][8];
+  const int g = warp >> 2, pq = warp & 3;
+  float acc[16];
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
   for (int tap = 0; tap < 9; ++tap) {
     __syncthreads();
     // weights of this tap: [2][64][32] <- wf[g][tap][ci][o]
@@ -719,10 +802,10 @@ __global__ void __launch_bounds__(256) conv1_ring_kernel(const __nv_bfloat16* __
       const int gg = i / 512, rem = i % 512;
       reinterpret_cast<float4*>(sW)[i] = __ldg(reinterpret_cast<const float4*>(wf + ((long long)(gg * 9 + tap) * 64) * 32) + rem);
     }
-    // upsampled input of this tap: 64 px x 16 channel octets
+    // upsampled input of this tap: 64 px x 16 channel octets (the 16 octets of a pixel on consecutive lanes)
     const int ky = tap / 3 - 1, kx = tap % 3 - 1;
     for (int i = tid; i < kRingPx * 16; i += 256) {
-      const int px = i & (kRingPx - 1), c8 = i / kRingPx;
+      const int c8 = i & 15, px = i >> 4;
       const int y = s_y[px] + ky, x = s_x[px] + kx;
       float u[8];
 #pragma unroll
@@ -736,8 +819,8 @@ __global__ void __launch_bounds__(256) conv1_ring_kernel(const __nv_bfloat16* __
         const int yy[4] = {y0, y0, y1, y1}, xx[4] = {x0, x1, x0, x1};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const long long o = (((long long)b * H + yy[k]) * W + xx[k]) * 128 + c8 * 8;
-          const uint4 h = __ldg(reinterpret_cast<const uint4*>(chi + o)), l = __ldg(reinterpret_cast<const uint4*>(clo + o));
+          const unsigned o = ((unsigned)(b * H + yy[k]) * (unsigned)W + (unsigned)xx[k]) * 16u + (unsigned)c8;      // uint4 units
+          const uint4 h = __ldg(reinterpret_cast<const uint4*>(chi) + o), l = __ldg(reinterpret_cast<const uint4*>(clo) + o);
           const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -747,58 +830,56 @@ __global__ void __launch_bounds__(256) conv1_ring_kernel(const __nv_bfloat16* __
           }
         }
       }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) sU[(c8 * 8 + e) * kRingPx + px] = u[e];
+      float4* d = reinterpret_cast<float4*>(sU + px * 128 + c8 * 8);
+      d[0] = make_float4(u[0], u[1], u[2], u[3]);
+      d[1] = make_float4(u[4], u[5], u[6], u[7]);
     }
     __syncthreads();
-    const float* su = sU + g * 64 * kRingPx;
-    const float* sw = sW + g * 64 * 32 + oq * 8;
-#pragma unroll 4
-    for (int ci = 0; ci < 64; ++ci) {
-      const float u0 = su[ci * kRingPx + lane], u1 = su[ci * kRingPx + lane + 32];
-      const float4 w0 = *reinterpret_cast<const float4*>(sw + ci * 32), w1 = *reinterpret_cast<const float4*>(sw + ci * 32 + 4);
-      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    const float* su = sU + (pq * 16) * 128 + g * 64;
+    const float* sw = sW + g * 64 * 32 + lane;
+#pragma unroll 2
+    for (int c4 = 0; c4 < 16; ++c4) {
+      const float w0 = sw[(4 * c4) * 32], w1 = sw[(4 * c4 + 1) * 32], w2 = sw[(4 * c4 + 2) * 32], w3 = sw[(4 * c4 + 3) * 32];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { acc[0][j] = fmaf(u0, wv[j], acc[0][j]); acc[1][j] = fmaf(u1, wv[j], acc[1][j]); }
+      for (int j = 0; j < 16; ++j) {
+        const float4 uv = *reinterpret_cast<const float4*>(su + j * 128 + 4 * c4);      // same address on every lane: broadcast
+        acc[j] = fmaf(uv.x, w0, acc[j]); acc[j] = fmaf(uv.y, w1, acc[j]);
+        acc[j] = fmaf(uv.z, w2, acc[j]); acc[j] = fmaf(uv.w, w3, acc[j]);
+      }
     }
   }
-  // bias + ReLU, conv1 output (when kept), partial prediction dots
-  const float* pw = g == 0 ? pg_w : pl_w;
-  const int pnc = g == 0 ? 2 : 1;
+  // bias + ReLU, conv1 output (when kept: 128 contiguous bytes per pixel and head), rectified features to shared memory for the tail
+  __syncthreads();                                 // every warp is done reading sU
+  float* sV = sU;                                  // [64 px][65]
+  const float bv = __ldg(bias + g * 32 + lane);
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int px = lane + 32 * i, y = s_y[px], x = s_x[px];
-    float p0 = 0.f, p1 = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int o = oq * 8 + j;
-      acc[i][j] = fmaxf(acc[i][j] + __ldg(bias + g * 32 + o), 0.f);
-      if (pw) { p0 = fmaf(acc[i][j], __ldg(pw + o), p0); if (pnc > 1) p1 = fmaf(acc[i][j], __ldg(pw + 32 + o), p1); }
-    }
-    if (y >= 0 && out) {
-      float* op = out + (((long long)b * H2 + y) * W2 + x) * 64 + g * 32 + oq * 8;
-      *reinterpret_cast<float4*>(op) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-      *reinterpret_cast<float4*>(op + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
-    }
-    if (pw) {
-      if (g == 0) { sP[(px * 3 + 0) * 4 + oq] = p0; sP[(px * 3 + 1) * 4 + oq] = p1; }
-      else sP[(px * 3 + 2) * 4 + oq] = p0;
-    }
+  for (int j = 0; j < 16; ++j) {
+    const int px = pq * 16 + j, y = s_y[px], x = s_x[px];
+    const float v = fmaxf(acc[j] + bv, 0.f);
+    if (y >= 0 && out) out[(((long long)b * H2 + y) * W2 + x) * 64 + g * 32 + lane] = v;
+    sV[px * 65 + g * 32 + lane] = v;
   }
   if (!pg_w) return;
   __syncthreads();
+  // fused prediction tail of the regression heads: 1x1 conv 32 -> 2 (gravity) / 1 (latitude), bias first then channels in order
+  // (the fma chain of pred_tail_kernel), normalise / clamp
   if (tid < kRingPx && s_y[tid] >= 0) {
-    const float* q = sP + tid * 12;
+    const float* f = sV + tid * 65;
+    float v0 = __ldg(pg_b), v1 = __ldg(pg_b + 1), vl = __ldg(pl_b);
+#pragma unroll 8
+    for (int c = 0; c < 32; ++c) {
+      v0 = fmaf(f[c], __ldg(pg_w + c), v0);
+      v1 = fmaf(f[c], __ldg(pg_w + 32 + c), v1);
+      vl = fmaf(f[32 + c], __ldg(pl_w + c), vl);
+    }
     const long long HW2 = (long long)H2 * W2, pix = (long long)s_y[tid] * W2 + s_x[tid];
-    const float v0 = __ldg(pg_b) + ((q[0] + q[1]) + (q[2] + q[3])), v1 = __ldg(pg_b + 1) + ((q[4] + q[5]) + (q[6] + q[7]));
-    const float vl = __ldg(pl_b) + ((q[8] + q[9]) + (q[10] + q[11]));
     const float nrm = fmaxf(sqrtf(v0 * v0 + v1 * v1), 1e-12f);
     float* po = pg_out + (long long)b * 2 * HW2 + pix;
     po[0] = v0 / nrm; po[HW2] = v1 / nrm;
     pl_out[(long long)b * HW2 + pix] = fminf(fmaxf(vl, -1.f), 1.f);
   }
 }
-constexpr int kRingSmem = (128 * kRingPx + 2 * 64 * 32 + kRingPx * 12) * 4;
+constexpr int kRingSmem = (128 * kRingPx + 2 * 64 * 32) * 4;
 
 // Bin decode shared by the two classification kernels (utils/utils.py:114-130 and :148-162).
 __device__ __forceinline__ void decode_bin_store(float* __restrict__ field, int b, int r, int HW, int NC, int bi, int is_gravity) {

@@ -750,7 +750,7 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
     const long long m = ar.mark();
     const long long M = (long long)n * 160 * 160;
     SplitT col = F.salloc(M, 160);
-    if (!dry) LAUNCHED(launch_pdl(stem_gather_kernel, dim3(ew_grid(M * 20)), dim3(256), 0, st, x0, col.hi, col.lo, n, 160, 160, 2));
+    if (!dry) LAUNCHED(launch_pdl(stem_gather_kernel, dim3(ew_grid(stem_gather_threads(n, 160, 160))), dim3(256), 0, st, x0, col.hi, col.lo, n, 160, 160, 2));
     Epi o; o.S = ll; o.act = 1;
     TRY(F.tgemm(col, M, 160, 0, e->llencg, 64, o));
     ar.release(m);
@@ -783,7 +783,7 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
     if (s == 0 && e->use_stem_tc) {
       const long long mm = ar.mark();
       SplitT col = F.salloc(rows, 160);
-      if (!dry) LAUNCHED(launch_pdl(stem_gather_kernel, dim3(ew_grid(rows * 20)), dim3(256), 0, st, x0, col.hi, col.lo, n, 80, 80, 4));
+      if (!dry) LAUNCHED(launch_pdl(stem_gather_kernel, dim3(ew_grid(stem_gather_threads(n, 80, 80))), dim3(256), 0, st, x0, col.hi, col.lo, n, 80, 80, 4));
       Epi o; o.C = tf; o.ldc = C;
       TRY(F.tgemm(col, rows, 160, 0, e->embed1g, 64, o));
       ar.release(mm);
@@ -835,7 +835,7 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
       TRY(F.tapf(x, rows * C, "mit.s%d.b%d.attn", s + 1, i));
       TRY(F.ln_split(x, t1, rows, C, b.ln2, 1e-6f));
       { Epi o; o.C = h1; o.ldc = 4 * C; TRY(F.tgemm(t1, rows, C, 0, b.fc1, 4 * C, o)); }
-      if (!dry) LAUNCHED(launch_pdl(dwconv3x3_gelu_kernel, dim3(ew_grid((long long)n * ((R + 1) / 2) * ((R + 3) / 4) * C)), dim3(256), 0, st, h1, nullptr, n, R, R, 4 * C, b.dw_w, b.dw_b, h2.hi, h2.lo));
+      if (!dry) LAUNCHED(launch_pdl(dwconv3x3_gelu_kernel, dim3(ew_grid((long long)n * ((R + 1) / 2) * ((R + PF_DW3_PX - 1) / PF_DW3_PX) * C)), dim3(256), 0, st, h1, nullptr, n, R, R, 4 * C, b.dw_w, b.dw_b, h2.hi, h2.lo));
       { Epi o; o.C = x; o.ldc = C; o.res = x; o.ldr = C; TRY(F.tgemm(h2, rows, 4 * C, 0, b.fc2, C, o)); }
       TRY(F.tapf(x, rows * C, "mit.s%d.b%d", s + 1, i));
     }
@@ -966,7 +966,7 @@ static int run_forward_tma(Fwd& F, const pf_batch* bt) {
         if (e->use_dwln) {   // depthwise 7x7 + LayerNorm in one kernel, straight to the split planes pwconv1 loads
           if (!dry) LAUNCHED(dwconv7x7_ln_launch(x, n, r, r, C, b.dw_w, b.dw_b, b.ln.w, b.ln.b, 1e-6f, y, st));
         } else {
-          if (!dry) LAUNCHED(launch_pdl(dwconv7x7_kernel, dim3(ew_grid((long long)n * ((r + 1) / 2) * ((r + 7) / 8) * (C / 4))), dim3(256), 0, st, x, yf, n, r, r, C, b.dw_w, b.dw_b));
+          if (!dry) LAUNCHED(launch_pdl(dwconv7x7_kernel, dim3(ew_grid((long long)n * ((r + 1) / 2) * ((r + PF_DW7_PX - 1) / PF_DW7_PX) * (C / 4))), dim3(256), 0, st, x, yf, n, r, r, C, b.dw_w, b.dw_b));
           TRY(F.ln_split(yf, y, rows, C, b.ln, 1e-6f));
         }
         { Epi o; o.S = h; o.act = 2; TRY(F.tgemm(y, rows, C, 0, b.pw1, 4 * C, o)); }
@@ -1163,6 +1163,12 @@ int pf_profile_kernels_read(pf_handle h, char* buf, int cap) {
     const char* e = c;
     while (*e && (isalnum((unsigned char)*e) || *e == '_')) ++e;
     std::string name(c, e);
+    if (name == "launch_pdl" && *e == '(') {   // launch_pdl(kernel, grid, ...): the kernel is the first argument
+      c = e + 1;
+      e = c;
+      while (*e && (isalnum((unsigned char)*e) || *e == '_')) ++e;
+      name.assign(c, e);
+    }
     // template arguments of direct kernel launches distinguish the variants (e.g. stem_conv_launch<7, 7, 2, 3, 64>)
     if (*e == '<' && e[1] != '<') { const char* t = strchr(e, '>'); if (t) name.append(e, t + 1); }
     auto it = agg.find(name);
@@ -1567,12 +1573,12 @@ int pf_op_attention_tc(const float* q, const float* kv, float* out, int B, int N
 }
 int pf_op_dwconv3x3_gelu(const float* x, float* y, int B, int H, int W, int C, const float* w, const float* bias, void* stream) {
   if (C % 4) return fail(PF_ERR_ARG, "C %% 4");
-  LAUNCHED(launch_pdl(dwconv3x3_gelu_kernel, dim3(ew_grid((long long)B * ((H + 1) / 2) * ((W + 3) / 4) * (C / 4))), dim3(256), 0, (cudaStream_t)stream, x, y, B, H, W, C, w, bias, nullptr, nullptr));
+  LAUNCHED(launch_pdl(dwconv3x3_gelu_kernel, dim3(ew_grid((long long)B * ((H + 1) / 2) * ((W + PF_DW3_PX - 1) / PF_DW3_PX) * (C / 4))), dim3(256), 0, (cudaStream_t)stream, x, y, B, H, W, C, w, bias, nullptr, nullptr));
   return PF_OK;
 }
 int pf_op_dwconv7x7(const float* x, float* y, int B, int H, int W, int C, const float* w, const float* bias, void* stream) {
   if (C % 4) return fail(PF_ERR_ARG, "C %% 4");
-  LAUNCHED(launch_pdl(dwconv7x7_kernel, dim3(ew_grid((long long)B * ((H + 1) / 2) * ((W + 7) / 8) * (C / 4))), dim3(256), 0, (cudaStream_t)stream, x, y, B, H, W, C, w, bias));
+  LAUNCHED(launch_pdl(dwconv7x7_kernel, dim3(ew_grid((long long)B * ((H + 1) / 2) * ((W + PF_DW7_PX - 1) / PF_DW7_PX) * (C / 4))), dim3(256), 0, (cudaStream_t)stream, x, y, B, H, W, C, w, bias));
   return PF_OK;
 }
 int pf_op_upsample2x(const float* x, float* y, int B, int H, int W, int C, void* stream) {
