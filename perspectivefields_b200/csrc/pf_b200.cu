@@ -368,7 +368,7 @@ struct Fwd {
     return gemm_tma_launch(MODE_HALO, maps, p, bn, kb, sms, st, pred);
   }
   int launch_tma(int mode, const TmaMaps& maps, const TmaGemmParams& p, const PredTail* pred = nullptr) {
-    const int bn = tma_pick_bn(p.N, mode), kb = tma_pick_kb(bn, p.K, mode);
+    const int bn = mode == MODE_GEMM ? tma_pick_bn_gemm(p.M, p.N, p.K, e->sm_count) : tma_pick_bn(p.N, mode), kb = tma_pick_kb(bn, p.K, mode);
     if (e->profile) {
       pf_engine::ProfRec r{};
       for (cudaEvent_t* ev : {&r.a, &r.b}) {
@@ -438,7 +438,7 @@ struct Fwd {
     fill_epi(p, w, o, 0);
     if (const char* d = getenv("PF_GEMM_DBG")) p.dbg = atoi(d);      // timing experiments only (gemm_tma.cuh: TmaGemmParams::dbg)
     TmaMaps maps{};
-    const int bn = tma_pick_bn(N, MODE_GEMM);
+    const int bn = tma_pick_bn_gemm(M, N, K, e->sm_count);
     // CTA-pair kernel (256 x BN tiles, tcgen05.mma.cta_group::2: half the weight traffic per SM) when there are enough pair tiles
     const int pair_clusters = (e->use_pair && !getenv("PF_NO_PAIR")) ? gemm2_plan(e->device, (int)M, N, bn) : 0;
     const int kb = pair_clusters ? 32 : tma_pick_kb(bn, K, MODE_GEMM);

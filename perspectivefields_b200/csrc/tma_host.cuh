@@ -82,6 +82,28 @@ inline int tma_pick_bn(int N, int mode) {
   return bn;
 }
 
+// GEMM mode with the number of rows known.  The widest tile moves the fewest operand bytes per output column (GEMM mode is bound
+// by L2 -> shared-memory operand traffic: about 1.6 clk per operand row and K step of 16 on a full machine, measured -- a 128 x 256
+// tile costs 614 clk per K step against 384 clk of MMA), so it wins whenever the tiles fill the machine.  A launch that leaves
+// most SMs idle (stage-4 / spatially reduced layers: 25 row tiles) is faster with narrower tiles spread over more SMs: pick the
+// width that minimises waves x time per tile in that model.  Results do not depend on the choice (same K order per output).
+inline int tma_pick_bn_gemm(long long M, int N, int K, int sm_count) {
+  const int base = tma_pick_bn(N, MODE_GEMM);
+  static const int policy = getenv("PF_BN_POLICY") ? atoi(getenv("PF_BN_POLICY")) : 1;     // 0: always the widest tile (A/B runs)
+  const long long mt = cdivl(M, 128);
+  if (!policy || mt * cdiv(N, base) * 4 > 3LL * sm_count) return base;
+  int best = base;
+  double best_cost = 1e30;
+  for (int bn = base; bn >= 32; bn -= 32) {
+    const long long tiles = mt * cdiv(N, bn);
+    const double waves = (double)cdivl(tiles, sm_count);
+    const double mma = 3.0 * (bn / 2 > 32 + bn / 4 ? bn / 2 : 32 + bn / 4), load = 1.6 * (128 + bn);
+    const double cost = waves * ((K / 16) * (mma > load ? mma : load) + 3000.0);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
 // K elements per pipeline step: 64 for narrow tiles when K allows it (halo mode: BN <= 128; GEMM mode, whose stages also
 // hold the A tile and whose epilogue staging takes 72 KB: BN <= 64), else 32
 inline int tma_pick_kb(int bn, int K, int mode) {
