@@ -57,7 +57,8 @@ struct TmaGemmParams {
   // bit 1 = producer re-arms the stages without loading (operands stay whatever the first pass loaded), bit 2 = no MMAs issued,
   // bit 3 = epilogue without the TMEM read, bit 4 = no fence.proxy.async, bit 5 = no bulk wait, bit 6 = no bias staging,
   // bit 7 = the epilogue only waits and releases the accumulator, bit 8 = producer / MMA warps poll their barriers
-  // (test_wait) instead of the suspending try_wait, bit 9 = the epilogue warps too.  Results are then meaningless; only the kernel duration is of interest.
+  // (test_wait) instead of the suspending try_wait, bit 9 = the epilogue warps too, bit 10 = (halo mode) the halo producer re-arms its
+  // buffers without loading.  Bits 0, 1, 2, 7 act in halo mode as well (env PF_HALO_DBG).  Results are then meaningless; only the kernel duration is of interest.
   int dbg;
 };
 
@@ -205,7 +206,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
         for (int kc = 0; kc < nk; ++kc, ++it) {
           const int s = it % NS;
           if (p.dbg & 256) mbar_wait_spin(empty_b(s), ((it / NS) & 1) ^ 1); else mbar_wait(empty_b(s), ((it / NS) & 1) ^ 1);
-          if (MODE == MODE_GEMM && (p.dbg & 2) && it >= NS) { mbar_arrive(full_b(s)); continue; }
+          if ((p.dbg & 2) && it >= NS) { mbar_arrive(full_b(s)); continue; }
           mbar_expect_tx(full_b(s), Cfg::kStage);
           const uint32_t st = ring + s * Cfg::kStage;
           int kcol;
@@ -234,6 +235,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
         for (int c = 0; c < nchunks; ++c, ++ita) {
           const int buf = ita & 1;
           mbar_wait(empty_a(buf), ((ita >> 1) & 1) ^ 1);
+          if ((p.dbg & 1024) && ita >= 2) { mbar_arrive(full_a(buf)); continue; }
           mbar_expect_tx(full_a(buf), 2 * kHaloBytes);
           const uint32_t dst = a_base + buf * Cfg::kABuf;
           const int ci = c * 64;
@@ -286,7 +288,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
           uint64_t dbl = dbh + (uint64_t)(Cfg::kBPlane >> 4);
 #pragma unroll
           for (int kk = 0; kk < KB / 16; ++kk) {
-            if (MODE == MODE_GEMM && (p.dbg & 4)) break;
+            if (p.dbg & 4) break;
             if (Cfg::kDual) {
               umma_bf16(acc, dah, dbh, Cfg::kIdesc2, (kc | kk) ? 1u : 0u);     // (D1 | D2) (+)= a_hi x [b_hi ; b_lo]
               umma_bf16(acc, dal, dbh, Cfg::kIdesc, 1u);                       //  D1        += a_lo x b_hi
@@ -469,6 +471,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
       tc_fence_after();
 #pragma unroll 1
       for (int ch = eh; ch < BN / 32; ch += 2) {
+        if (p.dbg & 128) break;
         uint32_t v[32];
         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * Cfg::kAccCols + ch * 32), v);
         if (Cfg::kDual) {       // second half of the accumulator pair: the a_hi x b_lo products
@@ -482,7 +485,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
         // output row / first output column of this chunk (phase mode: hi-res pixel of phase `ch`, channels 0-31)
         const long long mo = ph4 ? ((long long)bimg * 2 * p.H + 2 * oy + (ch >> 1)) * (2 * p.W) + 2 * ox + (ch & 1) : m;
         const int nbo = ph4 ? 0 : nb;
-        if (valid && nb < p.N) {
+        if (valid && nb < p.N && !(p.dbg & 1)) {
           float o[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]);

@@ -493,6 +493,7 @@ struct Fwd {
     p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.N = N; p.K = 9 * Cin; p.a_c0 = a_c0; p.a_gc = a_gc; p.groups = groups;
     p.c_split = A2 ? c_split : 0; p.a2_c0 = a2_c0;
     fill_epi(p, w, o, bias_gstride);
+    if (const char* d = getenv("PF_HALO_DBG")) p.dbg = atoi(d);      // timing experiments only (gemm_tma.cuh: TmaGemmParams::dbg)
     TmaMaps maps{};
     const int bn = tma_pick_bn(N, MODE_HALO), kb = tma_pick_kb(bn, p.K, MODE_HALO);
     const char* msg = nullptr;
