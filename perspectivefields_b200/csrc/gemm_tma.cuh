@@ -84,8 +84,8 @@ template <int BN, int MODE, int KB> struct TmaCfg {
   static constexpr int kStagesRaw = kBudget / kStage;
   static constexpr int kStages = kStagesRaw > 16 ? 16 : kStagesRaw;
   static constexpr int kSmemBytes = (MODE == MODE_HALO ? 2 * kABuf : 0) + kStages * kStage + kEpiStage + kEpiVec + 512 + 1024;
-  // Narrow halo tiles (BN <= 128): every tcgen05.mma narrower than N ~ 192 costs the same ~93 cycles (it is bound by reading its
-  // 128 x 16 A slice from shared memory), so the three MMAs per product are folded into TWO: a_hi x [b_hi ; b_lo] as ONE MMA of
+  // Narrow halo tiles (BN <= 128): a tcgen05.mma costs max(N / 2, 32 + N / 4) clk (tools/mma_rate.cu: below N = 128 it is bound by
+  // fetching its 128 x 16 A slice and B from shared memory), so the three MMAs per product are folded into TWO: a_hi x [b_hi ; b_lo] as ONE MMA of
   // width 2 BN (the hi and lo weight planes of a pipeline step are adjacent in shared memory) into an accumulator pair
   // (D1 | D2), and a_lo x b_hi into D1; the epilogue adds D1 + D2.  Same products, one A-slice read less per K step.
   static constexpr bool kDual = MODE == MODE_HALO && BN <= 128;
