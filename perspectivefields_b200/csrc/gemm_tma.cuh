@@ -25,6 +25,9 @@
 
 namespace pf {
 
+#ifndef PF_EPI_PAIR_STORE
+#define PF_EPI_PAIR_STORE 1      // halo-mode epilogue: lane pairs write 32 contiguous bytes per store (0 = 16 bytes per lane and row)
+#endif
 constexpr int MODE_GEMM = 0, MODE_HALO = 1;
 constexpr int kTmaThreads = 384;   // warps 0-3: TMA / MMA / TMEM-alloc+halo / idle;  warps 4-11: epilogue (two per TMEM lane quarter)
 constexpr int kHaloBytes = 180 * 128;   // one bf16 plane of an 18 x 10 pixel x 64 channel halo (what one TMA box delivers)
@@ -485,10 +488,11 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
         // output row / first output column of this chunk (phase mode: hi-res pixel of phase `ch`, channels 0-31)
         const long long mo = ph4 ? ((long long)bimg * 2 * p.H + 2 * oy + (ch >> 1)) * (2 * p.W) + 2 * ox + (ch & 1) : m;
         const int nbo = ph4 ? 0 : nb;
-        if (valid && nb < p.N && !(p.dbg & 1)) {
-          float o[32];
+        const bool chunk_ok = nb < p.N && !(p.dbg & 1);      // warp-uniform
+        float o[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]);
+        for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]);
+        if (valid && chunk_ok) {
           if (p.bias_mode) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -548,6 +552,63 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
               po[0] = fminf(fmaxf(v0, -1.f), 1.f);
             }
           }
+        }
+#if PF_EPI_PAIR_STORE
+        // Stores.  A thread owns one pixel row of the chunk (128 B of fp32, 64 B per bf16 plane); storing it 16 bytes at a time makes
+        // every warp-wide store touch 32 half-filled sectors, and the short-K launches were bound by exactly that (r02 notes:
+        // 494 us against 233 us of main loop).  The two lanes of an x-adjacent pixel pair exchange halves so that each store
+        // instruction writes 32 contiguous bytes per pair: full sectors, half as many per request.
+        if (chunk_ok && (p.C || p.Shi)) {
+          const bool odd = lane & 1;
+          const bool valid_p = __shfl_xor_sync(0xffffffffu, (int)valid, 1) != 0;
+          const long long mo_p = mo + (odd ? -1 : 1) * (ph4 ? 2 : 1);       // the partner's pixel: same image row, x +- 1
+          const long long moA = odd ? mo_p : mo, moB = odd ? mo : mo_p;     // row A = the even lane's pixel, row B = the odd lane's
+          const bool vA = odd ? valid_p : valid, vB = odd ? valid : valid_p;
+          if (p.C) {
+            float* cA = p.C + moA * p.ldc + p.c_coff + g * p.c_gcoff + nbo + (odd ? 4 : 0);
+            float* cB = p.C + moB * p.ldc + p.c_coff + g * p.c_gcoff + nbo + (odd ? 4 : 0);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {      // float4 slots 2t (even lane) and 2t + 1 (odd lane) of both rows
+              float k[4], r[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                k[e] = odd ? o[8 * t + 4 + e] : o[8 * t + e];
+                r[e] = __shfl_xor_sync(0xffffffffu, odd ? o[8 * t + e] : o[8 * t + 4 + e], 1);
+              }
+              if (vA) *reinterpret_cast<float4*>(cA + 8 * t) = odd ? make_float4(r[0], r[1], r[2], r[3]) : make_float4(k[0], k[1], k[2], k[3]);
+              if (vB) *reinterpret_cast<float4*>(cB + 8 * t) = odd ? make_float4(k[0], k[1], k[2], k[3]) : make_float4(r[0], r[1], r[2], r[3]);
+            }
+          }
+          if (p.Shi) {
+            const long long sA = moA * p.lds + p.s_coff + g * p.s_gcoff + nbo + (odd ? 8 : 0);
+            const long long sB = moB * p.lds + p.s_coff + g * p.s_gcoff + nbo + (odd ? 8 : 0);
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {      // 8-column slots 2t (even lane) and 2t + 1 (odd lane) of both rows
+              float k[8], r[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float mine = odd ? o[16 * t + 8 + e] : o[16 * t + e], give = odd ? o[16 * t + e] : o[16 * t + 8 + e];
+                k[e] = p.split_relu ? fmaxf(mine, 0.f) : mine;
+                r[e] = __shfl_xor_sync(0xffffffffu, p.split_relu ? fmaxf(give, 0.f) : give, 1);
+              }
+              uint4 kh, kl, rh, rl;
+              split_bf16x2(k[0], k[1], kh.x, kl.x); split_bf16x2(k[2], k[3], kh.y, kl.y);
+              split_bf16x2(k[4], k[5], kh.z, kl.z); split_bf16x2(k[6], k[7], kh.w, kl.w);
+              split_bf16x2(r[0], r[1], rh.x, rl.x); split_bf16x2(r[2], r[3], rh.y, rl.y);
+              split_bf16x2(r[4], r[5], rh.z, rl.z); split_bf16x2(r[6], r[7], rh.w, rl.w);
+              if (vA) {
+                *reinterpret_cast<uint4*>(p.Shi + sA + 16 * t) = odd ? rh : kh;
+                *reinterpret_cast<uint4*>(p.Slo + sA + 16 * t) = odd ? rl : kl;
+              }
+              if (vB) {
+                *reinterpret_cast<uint4*>(p.Shi + sB + 16 * t) = odd ? kh : rh;
+                *reinterpret_cast<uint4*>(p.Slo + sB + 16 * t) = odd ? kl : rl;
+              }
+            }
+          }
+        }
+#else
+        if (valid && chunk_ok) {
           if (p.C) {
             float* cp = p.C + mo * p.ldc + p.c_coff + g * p.c_gcoff + nbo;
 #pragma unroll
@@ -568,6 +629,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gemm_tma_kernel(const __grid_c
             }
           }
         }
+#endif
       }
       tc_fence_before();
       mbar_arrive(tmem_empty(as));
